@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the DistEGNN hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload synth1m]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete FastEGNN forward (4 layers, all virtual-node all-reduces) over the WHOLE graph
+(all partitions concurrently, one per GPU), inputs resident in HBM, CSR preprocessing cached.
+metric = graph-steps/s (BASELINE.json), `edges_per_sec` = Σ_p E_p × graph-steps/s.
+
+  value     device-timed (CUDA events, max over ranks), inputs resident, L2 flushed between steps
+  e2e       same metric through the public API with HOST (pinned) inputs: H2D of every input, CSR build,
+            forward, D2H of both outputs inside the timed region
+  roofline  the edge-aggregation kernel (dominant): algorithmic bytes E·284+N·536 per launch ÷ its
+            CUDA-event duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port of the reference's CPU PyTorch path on this box's host cores, on a
+            bounded sample of the same workload (rank 0, N=1 only)
+
+--impl reference times ONLY that CPU path (the reference itself is Python and cannot travel to the
+GPU box; the oracle replays its ATen op sequence — see oracle/fastegnn_oracle.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from distegnn_b200 import synth  # noqa: E402
+
+METRIC = "graph_steps_per_sec"
+UNIT = "graph-steps/s"
+N_LAYERS = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synth1m", choices=list(synth.WORKLOADS))
+    ap.add_argument("--split-mode", default="random", choices=["random", "kmeans"])
+    ap.add_argument("--nodes", type=int, default=None, help="override node count (debug)")
+    ap.add_argument("--cpu-sample-nodes", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def edge_kernel_bytes(n_nodes: int, n_edges: int) -> int:
+    """Algorithmic bytes of one edge-stage launch: per edge row+col ids 8 B, edge_attr 8 B,
+    neighbour feature row 256 B, neighbour coordinate 12 B; per node own feature row + coordinate read
+    268 B and the aggregated [64]+[3] written 268 B."""
+    return n_edges * 284 + n_nodes * 536
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of this rank's GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason")
+                 or k.startswith("nvmlClocksThrottleReason")}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and mask & bit:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace(
+                            "nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        reasons = sorted(r for r in self.reasons if r not in ("None", "GpuIdle", "ApplicationsClocksSetting"))
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(s)}
+
+
+def model_dims(w: synth.Workload):
+    return dict(node_feat_nf=w.node_feat_nf, node_attr_nf=w.node_attr_nf, edge_attr_nf=w.edge_attr_nf,
+                virtual_channels=w.virtual_channels, n_layers=N_LAYERS, normalize=w.normalize)
+
+
+def make_state_dict(w: synth.Workload):
+    """Random-init weights of the architecture (same distributions as the reference's init)."""
+    from distegnn_b200 import FastEGNN
+    torch.manual_seed(0)
+    m = FastEGNN(hidden_nf=64, world_size=1, **model_dims(w))
+    return m.state_dict()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference's PyTorch path on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_time(w: synth.Workload, sd, sample_nodes: int, repeats: int):
+    """Best-of-`repeats` forward time of the oracle on a `sample_nodes` sub-cloud of the same density."""
+    from oracle import fastegnn_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = min(sample_nodes, w.n_nodes)
+    inp = synth.make_partitions(w, n_nodes=n, seed=0)[0]
+    e = int(inp["edge_index"].shape[1])
+    best = float("inf")
+    with torch.no_grad():
+        orc.forward(sd, **inp, normalize=w.normalize)          # warm-up
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            orc.forward(sd, **inp, normalize=w.normalize)
+            best = min(best, time.perf_counter() - t0)
+    return best, n, e, cores
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    sd = {k: v.clone() for k, v in make_state_dict(w).items()}
+    full_nodes = args.nodes or w.n_nodes
+    times = []
+    n = e = cores = None
+    # each "step" is one oracle forward over the bounded sample
+    for i in range(args.warmup + args.steps):
+        t, n, e, cores = cpu_reference_time(w, sd, args.cpu_sample_nodes, 1)
+        if i >= args.warmup:
+            times.append(t)
+    t_step = sum(times) / len(times)
+    edges_per_s = e / t_step
+    # equivalent whole-graph rate assuming time ∝ edges at fixed density (nodes scale along)
+    full_edges_est = e * (full_nodes / n)
+    value = edges_per_s / full_edges_est
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3 * (full_nodes / n),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "edges_per_sec": edges_per_s,
+        "config": {"workload": f"{w.name}: {full_nodes} nodes radius graph r={w.radius}, C={w.virtual_channels}, "
+                               f"{N_LAYERS} layers, hidden 64", "partitions": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "cpu": cpu_model_name(),
+                         "sample": f"oracle forward on a {n}-node/{e}-edge sub-cloud of the same density; "
+                                   f"rate scaled by node ratio {full_nodes / n:.1f}x to the full graph"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, w, rank, world, local_rank):
+    import torch.distributed as dist
+    from distegnn_b200 import FastEGNN
+    from distegnn_b200.backend import cuda_backend
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    full_nodes = args.nodes or w.n_nodes
+    t0 = time.perf_counter()
+    host = synth.make_partitions(w, world_size=world, split_mode=args.split_mode, seed=0,
+                                 n_nodes=full_nodes, only_rank=rank)[rank]
+    t_gen = time.perf_counter() - t0
+    pinned = {k: (v.pin_memory() if v is not None else None) for k, v in host.items()}
+    N, E = int(host["node_loc"].shape[0]), int(host["edge_index"].shape[1])
+
+    sd = make_state_dict(w)
+    model = FastEGNN(hidden_nf=64, world_size=world, **model_dims(w))
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    be = cuda_backend()
+    inp = {k: (v.to(dev) if v is not None else None) for k, v in host.items()}
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---- warm-up (also builds + caches the CSR) ----
+        t0 = time.perf_counter()
+        model(**inp)
+        torch.cuda.synchronize()
+        t_first = time.perf_counter() - t0
+        for _ in range(max(args.warmup - 1, 0)):
+            model(**inp)
+        # ---- timed: K steps, per-step CUDA events, L2 flushed between steps ----
+        sampler = ClockSampler(local_rank)
+        model._timing = []
+        evs = []
+        barrier()
+        sampler.start()
+        launches0 = be.launches
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush_buf.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out, X = model(**inp)
+            e.record()
+            evs.append((s, e))
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = be.launches - launches0
+        clocks = sampler.stop()
+        t_dev = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+        timing = model._timing
+        model._timing = None
+        t_edge = sum(t[1].elapsed_time(t[2]) for t in timing) * 1e-3 / max(len(timing), 1)
+        t_virt = sum(t[2].elapsed_time(t[3]) for t in timing) * 1e-3 / max(len(timing), 1)
+        t_node = sum(t[3].elapsed_time(t[4]) for t in timing) * 1e-3 / max(len(timing), 1)
+
+        # ---- e2e: host (pinned) inputs -> H2D -> CSR build -> forward -> D2H, every step ----
+        e2e = None
+        if not args.no_e2e:
+            h2d = sum(v.numel() * v.element_size() for v in pinned.values() if v is not None)
+            out_host = torch.empty(N, 3, dtype=torch.float32).pin_memory()
+            X_host = torch.empty(int(host["loc_mean"].shape[0]), 3, w.virtual_channels).pin_memory()
+            d2h = out_host.numel() * 4 + X_host.numel() * 4
+
+            def e2e_step():
+                d = {k: (v.to(dev, non_blocking=True) if v is not None else None) for k, v in pinned.items()}
+                o, xv = model(**d)
+                out_host.copy_(o, non_blocking=True)
+                X_host.copy_(xv, non_blocking=True)
+
+            e2e_step()
+            barrier()
+            n_e2e = max(3, min(args.steps, 5))
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            s.record()
+            for _ in range(n_e2e):
+                e2e_step()
+            e.record()
+            barrier()
+            t_e2e_wall = (time.perf_counter() - w0) / n_e2e
+            t_e2e = max(s.elapsed_time(e) * 1e-3 / n_e2e, 0.0)
+            t_e2e = max_over_ranks(max(t_e2e, 0.0))
+            e2e = {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+                   "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": t_e2e * 1e3,
+                   "wall_ms_per_step": max_over_ranks(t_e2e_wall) * 1e3,
+                   "includes": "H2D of all inputs from pinned host memory, CSR build, forward, D2H of outputs"}
+
+    t_step = max_over_ranks(t_dev / args.steps)
+    e_total = int(sum_over_ranks(E))
+    n_total = int(sum_over_ranks(N))
+    t_edge_max = max_over_ranks(t_edge)
+    peak, peak_src = peaks()
+    bytes_edge = edge_kernel_bytes(N, E)
+    achieved = bytes_edge / t_edge / 1e9 if t_edge > 0 else 0.0
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "edge_kernel_traffic.json")
+    if os.path.exists(tr_path) and world == 1:
+        try:
+            tj = json.load(open(tr_path))
+            if tj.get("workload") == w.name and tj.get("n_nodes") == full_nodes:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": 1.0 / t_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "edges_per_sec": e_total / t_step, "edge_layers_per_sec": e_total * N_LAYERS / t_step,
+            "config": {
+                "workload": f"{w.name}: {full_nodes} nodes radius graph r={w.radius} (expected degree "
+                            f"{w.degree}), C={w.virtual_channels}, F={w.node_feat_nf}, Na={w.node_attr_nf}, "
+                            f"{N_LAYERS} layers, hidden 64, normalize={w.normalize}",
+                "partitions": world, "split_mode": args.split_mode if world > 1 else "none",
+                "nodes_total": n_total, "edges_total_sum_p": e_total, "nodes_rank0": N, "edges_rank0": E,
+                "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events",
+                "csr": "cached (built once in warm-up; included in e2e)",
+                "graph_gen_s": round(t_gen, 2), "first_forward_s": round(t_first, 3)},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "edge_layer_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "bytes_per_launch": bytes_edge, "ms_per_launch": t_edge * 1e3, "peak_source": peak_src,
+                         "note": "rank-0 kernel; algorithmic bytes = E*284 + N*536 (SURVEY §8d)"},
+            "kernel_ms": {"edge": t_edge_max * 1e3, "virtual": max_over_ranks(t_virt) * 1e3,
+                          "node": max_over_ranks(t_node) * 1e3, "wall_ms_per_step": wall / args.steps * 1e3},
+        }
+    else:
+        line = None
+        max_over_ranks(t_virt)
+        max_over_ranks(t_node)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t, n, e, cores = cpu_reference_time(w, {k: v.cpu() for k, v in sd.items()}, args.cpu_sample_nodes, 2)
+        eps = e / t
+        full_edges_est = e * (full_nodes / n)
+        line["cpu_baseline"] = {
+            "value": eps / full_edges_est, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+            "edges_per_sec": eps, "sample_seconds": t,
+            "sample": f"oracle (reference op sequence, torch CPU fp32, {cores} threads) forward on a {n}-node/"
+                      f"{e}-edge sub-cloud of the same density, best of 2 after warm-up; rate scaled by "
+                      f"node ratio {full_nodes / n:.1f}x to the full graph"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    w = synth.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""The one place where torch tensors become raw device pointers for the C ABI.
+
+`CudaBackend` is the product path.  It has no CPU branch: tensors must live on a CUDA device and the
+shared library must load.  (tests/ contains a pure-torch stand-in with the same method names that is
+used ONLY to exercise the host-side sequencing and the multi-partition all-reduce logic under gloo on
+machines without a GPU; it is never importable from the package.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+Tensor = torch.Tensor
+
+
+class CudaBackend:
+    name = "cuda-sm100a"
+
+    def __init__(self) -> None:
+        self.lib = _lib.load()
+        self.launches = 0          # kernels of ours enqueued (bench.py reports it as gpu_launches)
+
+    # ---- helpers -------------------------------------------------------------------------------
+    @staticmethod
+    def _s(t: Tensor) -> int:
+        if not t.is_cuda:
+            raise _lib.DistEGNNError("distegnn_b200 has no CPU path: tensors must be on a CUDA device")
+        return _lib.stream_ptr(t.device)
+
+    # ---- graph preprocessing -------------------------------------------------------------------
+    def build_csr(self, edge_index: Tensor, n_nodes: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        E = int(edge_index.shape[1])
+        dev = edge_index.device
+        stream = self._s(edge_index)
+        rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+        row = torch.empty(E, dtype=torch.int32, device=dev)
+        col = torch.empty(E, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        nbytes = C.c_int64(0)
+        check(self.lib.distegnn_csr_workspace_bytes(n_nodes, E, C.byref(nbytes)), "csr_workspace_bytes")
+        ws = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=dev)
+        check(self.lib.distegnn_build_csr(ptr(edge_index), n_nodes, E, ptr(rowptr), ptr(row), ptr(col),
+                                          ptr(perm), ptr(ws), ws.numel(), stream), "build_csr")
+        self.launches += 5 if E else 1
+        return rowptr, row, col, perm
+
+    def gather_rows(self, src: Tensor, perm: Tensor) -> Tensor:
+        dst = torch.empty_like(src)
+        if src.numel():
+            check(self.lib.distegnn_gather_rows(ptr(src), ptr(perm), src.shape[0], src.shape[1], ptr(dst),
+                                                self._s(src)), "gather_rows")
+            self.launches += 1
+        return dst
+
+    # ---- layer stages --------------------------------------------------------------------------
+    def embed(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
+              Hn, vsum) -> None:
+        N, B, F, A, Cn, Na = dims
+        check(self.lib.distegnn_embed_fwd(N, B, F, A, Cn, Na, ptr(node_feat), ptr(node_loc),
+                                          ptr(data_batch), ptr(emb_wt), ptr(emb_b), ptr(layer0), ptr(h),
+                                          ptr(x4), ptr(batch32), ptr(P), ptr(Q), ptr(Hn), ptr(vsum),
+                                          self._s(h)), "embed_fwd")
+        self.launches += 1 if N else 0
+
+    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_fwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
+                                               ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m), ptr(agg_x),
+                                               self._s(x4)), "edge_layer_fwd")
+        self.launches += 1 if E else 0
+
+    def virtual_layer(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_layer_fwd(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
+                                                  ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
+                                                  ptr(vsum), self._s(x4)), "virtual_layer_fwd")
+        self.launches += 1 if N else 0
+
+    def node_layer(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
+                   lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum) -> None:
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_node_layer_fwd(N, B, A, Cn, Na, flags, ptr(rowptr), ptr(batch32), ptr(h),
+                                               ptr(x4), ptr(vel), ptr(attr), ptr(agg_m), ptr(agg_x),
+                                               ptr(agg_v), ptr(trans_v), ptr(lp), ptr(lp_next),
+                                               ptr(h_out), ptr(x4_out), ptr(P), ptr(Q), ptr(Hn),
+                                               ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd")
+        self.launches += 1 if N else 0
+
+    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G) -> None:
+        B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_update_fwd(B, A, Cn, Na, flags, ptr(vsum), ptr(Xv), ptr(Hv),
+                                                   ptr(lp), ptr(lp_next), ptr(G), self._s(vsum)),
+              "virtual_update_fwd")
+        self.launches += 1 if B else 0
+
+
+_cuda_backend: Optional[CudaBackend] = None
+
+
+def cuda_backend() -> CudaBackend:
+    global _cuda_backend
+    if _cuda_backend is None:
+        _cuda_backend = CudaBackend()
+    return _cuda_backend

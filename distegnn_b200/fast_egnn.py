@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's FastEGNN / DistEGNN model (models/FastEGNN.py).
+
+Same class name, constructor signature, ``forward`` signature, return tuple and ``state_dict`` keys as
+the reference, so ``main.py:61-62``, ``utils/train.py:63-71``, DDP wrapping and
+checkpoints work unchanged — but ``forward`` runs entirely in the hand-written sm_100a kernels behind
+the C ABI (include/distegnn_b200.h).  There is no eager/CPU fallback.
+
+Per forward (L layers) the device work is
+    embed → [all-reduce] → virtual_update(INIT)
+    L × { edge_layer, virtual_layer, node_layer → [all-reduce of the packed vsum] → virtual_update }
+i.e. ONE packed all-reduce per layer plus one up front (the reference issues 6 per layer, each behind
+host syncs: FastEGNN.py:196-197, 226-227, 260-261, 310-319).
+"""
+from __future__ import annotations
+
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+
+Tensor = torch.Tensor
+H = _lib.HIDDEN
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module/parameter names (they hold weights only — the
+# compute happens in the fused kernels)
+# --------------------------------------------------------------------------------------------------
+def _mlp(n_in: int, n_hidden: int, n_out: int, act: nn.Module, last_act: bool) -> nn.Sequential:
+    mods = [nn.Linear(n_in, n_hidden), act, nn.Linear(n_hidden, n_out)]
+    if last_act:
+        mods.append(act)
+    return nn.Sequential(*mods)
+
+
+def _coord_head(n_hidden: int, act: nn.Module) -> nn.Sequential:
+    # reference draws the 1-wide projection first, then the hidden layer (FastEGNN.py:96-103); keeping
+    # that order keeps `torch.manual_seed(s); FastEGNN(...)` weight-identical to the reference.
+    out = nn.Linear(n_hidden, 1, bias=False)
+    nn.init.xavier_uniform_(out.weight, gain=0.001)
+    return nn.Sequential(nn.Linear(n_hidden, n_hidden), act, out)
+
+
+class E_GCL_vel(nn.Module):
+    """Weights of one equivariant layer (reference E_GCL_vel, FastEGNN.py:46-141).  Not callable on its
+    own: the layer is executed by FastEGNN.forward through the fused kernels."""
+
+    def __init__(self, hidden_nf: int, node_attr_nf: int, edge_attr_nf: int, virtual_channels: int,
+                 act_fn: nn.Module):
+        super().__init__()
+        Hh, Cc = hidden_nf, virtual_channels
+        self.edge_mlp = _mlp(2 * Hh + 1 + edge_attr_nf, Hh, Hh, act_fn, True)           # φ_e
+        self.edge_mlp_virtual = _mlp(2 * Hh + 1 + Cc, Hh, Hh, act_fn, True)             # φ_ev
+        self.coord_mlp_r = _coord_head(Hh, act_fn)                                      # φ_x
+        self.coord_mlp_r_virtual = _coord_head(Hh, act_fn)                              # φ_xv
+        self.coord_mlp_v_virtual = _coord_head(Hh, act_fn)                              # φ_X
+        self.coord_mlp_vel = _mlp(Hh, Hh, 1, act_fn, False)                             # φ_v
+        self.node_mlp = _mlp(3 * Hh + node_attr_nf, Hh, Hh, act_fn, False)              # φ_h
+        self.node_mlp_virtual = _mlp(2 * Hh, Hh, Hh, act_fn, False)                     # φ_hv
+
+    def forward(self, *args, **kwargs):  # pragma: no cover
+        raise RuntimeError("E_GCL_vel layers are executed by FastEGNN.forward (fused CUDA path)")
+
+
+# --------------------------------------------------------------------------------------------------
+# packing of one layer's weights into the flat block the kernels read (include/distegnn_b200.h)
+# --------------------------------------------------------------------------------------------------
+def pack_layer_params(g: nn.Module, A: int, Cn: int, Na: int, device, offs: Dict[str, int],
+                      total: int) -> Tensor:
+    buf = torch.zeros(total, dtype=torch.float32, device=device)
+
+    def put(name: str, t: Tensor) -> None:
+        t = t.detach().to(device=device, dtype=torch.float32).reshape(-1)
+        buf[offs[name]:offs[name] + t.numel()] = t
+
+    W1, b1 = g.edge_mlp[0].weight, g.edge_mlp[0].bias            # [64, 2H+1+A]
+    put("E_W1A", W1[:, 0:H].t()); put("E_W1B", W1[:, H:2 * H].t()); put("E_W1R", W1[:, 2 * H])
+    if A:
+        put("E_W1E", W1[:, 2 * H + 1:2 * H + 1 + A].t())
+    put("E_B1", b1)
+    put("E_W2", g.edge_mlp[2].weight.t()); put("E_B2", g.edge_mlp[2].bias)
+    put("E_WC", g.coord_mlp_r[0].weight.t()); put("E_BC", g.coord_mlp_r[0].bias)
+    put("E_W3", g.coord_mlp_r[2].weight[0])
+    V1, vb1 = g.edge_mlp_virtual[0].weight, g.edge_mlp_virtual[0].bias   # [64, 2H+1+C]
+    put("V_W1H", V1[:, 0:H].t()); put("V_W1V", V1[:, H:2 * H].t()); put("V_W1R", V1[:, 2 * H])
+    put("V_W1M", V1[:, 2 * H + 1:2 * H + 1 + Cn].t()); put("V_B1", vb1)
+    put("V_W2", g.edge_mlp_virtual[2].weight.t()); put("V_B2", g.edge_mlp_virtual[2].bias)
+    put("V_WXV", g.coord_mlp_r_virtual[0].weight.t()); put("V_BXV", g.coord_mlp_r_virtual[0].bias)
+    put("V_W3XV", g.coord_mlp_r_virtual[2].weight[0])
+    put("V_WX", g.coord_mlp_v_virtual[0].weight.t()); put("V_BX", g.coord_mlp_v_virtual[0].bias)
+    put("V_W3X", g.coord_mlp_v_virtual[2].weight[0])
+    put("L_W", g.coord_mlp_vel[0].weight.t()); put("L_B", g.coord_mlp_vel[0].bias)
+    put("L_W3", g.coord_mlp_vel[2].weight[0]); put("L_B3", g.coord_mlp_vel[2].bias)
+    put("N_W1", g.node_mlp[0].weight.t()); put("N_B1", g.node_mlp[0].bias)
+    put("N_W2", g.node_mlp[2].weight.t()); put("N_B2", g.node_mlp[2].bias)
+    put("M_W1", g.node_mlp_virtual[0].weight.t()); put("M_B1", g.node_mlp_virtual[0].bias)
+    put("M_W2", g.node_mlp_virtual[2].weight.t()); put("M_B2", g.node_mlp_virtual[2].bias)
+    return buf
+
+
+class _GraphCache:
+    """CSR (sorted-by-destination) form of recent edge_index tensors.  Entries hold a strong reference
+    to the tensor they were built from, so its storage cannot be recycled under the same pointer; a hit
+    additionally requires an unchanged in-place version counter."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self.entries: "OrderedDict[int, tuple]" = OrderedDict()
+        self.builds = 0
+
+    def get(self, backend, edge_index: Tensor, n_nodes: int):
+        key = id(edge_index)
+        hit = self.entries.get(key)
+        if hit is not None and hit[0] is edge_index and hit[1] == edge_index._version and hit[2] == n_nodes:
+            self.entries.move_to_end(key)
+            return hit[3]
+        ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+        csr = backend.build_csr(ei, n_nodes)
+        self.builds += 1
+        self.entries[key] = (edge_index, edge_index._version, n_nodes, csr)
+        while len(self.entries) > self.capacity:
+            self.entries.popitem(last=False)
+        return csr
+
+
+# --------------------------------------------------------------------------------------------------
+# the model
+# --------------------------------------------------------------------------------------------------
+class FastEGNN(nn.Module):
+    """Drop-in for the reference ``models.FastEGNN.FastEGNN`` (FastEGNN.py:279-307)."""
+
+    def __init__(self, node_feat_nf, node_attr_nf, edge_attr_nf, hidden_nf, virtual_channels, world_size,
+                 act_fn=nn.SiLU(), n_layers=4, residual=True, attention=False, normalize=False, tanh=False,
+                 gravity=None):
+        super().__init__()
+        assert virtual_channels > 0, f'Channels of virtual node must greater than 0 (got {virtual_channels})'
+        if hidden_nf != H:
+            raise ValueError(f"distegnn_b200 kernels are built for hidden_nf={H} (got {hidden_nf})")
+        if not isinstance(act_fn, nn.SiLU):
+            raise ValueError("only act_fn=nn.SiLU() is supported (the reference never uses another)")
+        if attention or tanh or gravity is not None or not residual:
+            raise ValueError("attention/tanh/gravity/residual=False are never enabled by the reference "
+                             "(main.py:61-62) and are not implemented")
+        for name, v, hi in (("virtual_channels", virtual_channels, _lib.MAX_CHANNELS),
+                            ("edge_attr_nf", edge_attr_nf, _lib.MAX_EDGE_ATTR),
+                            ("node_attr_nf", node_attr_nf, _lib.MAX_NODE_ATTR),
+                            ("node_feat_nf", node_feat_nf, _lib.MAX_NODE_FEAT)):
+            if v > hi:
+                raise ValueError(f"{name}={v} exceeds the compiled limit {hi}")
+        self.hidden_nf = hidden_nf
+        self.n_layers = n_layers
+        self.node_feat_nf = node_feat_nf
+        self.node_attr_nf = node_attr_nf
+        self.edge_attr_nf = edge_attr_nf
+        self.virtual_channels = virtual_channels
+        self.world_size = world_size
+        self.normalize = normalize
+        # same construction order as the reference ⇒ same RNG stream ⇒ same initial weights
+        self.virtual_node_feat = nn.Parameter(data=torch.randn(size=(1, hidden_nf, virtual_channels)),
+                                              requires_grad=True)
+        self.embedding_in = nn.Linear(node_feat_nf, hidden_nf)
+        for i in range(n_layers):
+            self.add_module("gcl_%d" % i, E_GCL_vel(hidden_nf, node_attr_nf, edge_attr_nf,
+                                                    virtual_channels, act_fn))
+        # non-persistent runtime state
+        self._backend = None               # tests may inject a stand-in; default = CUDA C-ABI backend
+        self._graphs = _GraphCache()
+        self._packed = None                # (key, tensors)
+        self._timing = None                # bench.py: list collecting (name, start_evt, end_evt)
+        self._warned_grad = False
+        self.process_group = None          # torch.distributed group for the virtual-node sync (None = WORLD)
+
+    # ---- runtime helpers -----------------------------------------------------------------------
+    def _get_backend(self, device: torch.device):
+        if self._backend is not None:
+            return self._backend
+        if device.type != "cuda":
+            raise _lib.DistEGNNError(
+                "distegnn_b200.FastEGNN runs only on CUDA (sm_100a kernels); there is no CPU fallback — "
+                "move the model and inputs to a CUDA device")
+        from .backend import cuda_backend
+        return cuda_backend()
+
+    def _packed_params(self, device: torch.device):
+        params = list(self.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        A, Cn, Na = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf
+        offs, total = _lib.param_layout(A, Cn, Na)
+        layers = [pack_layer_params(getattr(self, "gcl_%d" % i), A, Cn, Na, device, offs, total)
+                  for i in range(self.n_layers)]
+        emb_wt = self.embedding_in.weight.detach().t().contiguous().to(device=device, dtype=torch.float32)
+        emb_b = self.embedding_in.bias.detach().contiguous().to(device=device, dtype=torch.float32)
+        hv0 = self.virtual_node_feat.detach()[0].t().contiguous().to(device=device, dtype=torch.float32)  # [C,64]
+        packed = dict(layers=layers, emb_wt=emb_wt, emb_b=emb_b, hv0=hv0)
+        self._packed = (key, packed)
+        return packed
+
+    def _sync_virtual(self, vsum: Tensor) -> None:
+        """weighted_average_reduce (FastEGNN.py:310-319) on the packed statistics: one SUM all-reduce;
+        the division by the summed node count happens in virtual_update."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(vsum, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def _mark(self, name: str):
+        if self._timing is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return (name, ev)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, node_feat, node_loc, node_vel, loc_mean, edge_index, data_batch, edge_attr=None,
+                node_attr=None) -> Tuple[Tensor, Tensor]:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned_grad:
+            warnings.warn("distegnn_b200.FastEGNN: the fused CUDA path is forward-only in this release; "
+                          "outputs are detached (backward = SURVEY §8 f-1).", stacklevel=2)
+            self._warned_grad = True
+        dev = node_loc.device
+        be = self._get_backend(dev)
+        A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
+        N, E, B = int(node_loc.shape[0]), int(edge_index.shape[1]), int(loc_mean.shape[0])
+        if node_feat.shape != (N, F) or node_vel.shape != (N, 3) or node_loc.shape != (N, 3):
+            raise ValueError(f"bad node tensor shapes: feat {tuple(node_feat.shape)}, loc "
+                             f"{tuple(node_loc.shape)}, vel {tuple(node_vel.shape)}; expected N={N}, F={F}")
+        if edge_index.shape[0] != 2 or edge_index.dtype != torch.int64:
+            raise ValueError("edge_index must be int64 [2,E]")
+        if data_batch.shape != (N,) or data_batch.dtype != torch.int64:
+            raise ValueError("data_batch must be int64 [N]")
+        if A > 0 and (edge_attr is None or edge_attr.shape != (E, A)):
+            raise ValueError(f"edge_attr must be [E,{A}]")
+        if Na > 0 and (node_attr is None or node_attr.shape != (N, Na)):
+            raise ValueError(f"node_attr must be [N,{Na}]")
+        if loc_mean.shape != (B, 3):
+            raise ValueError("loc_mean must be [B,3]")
+        K = 4 + 3 * Cn + H * Cn
+        f32 = lambda t: t.detach().to(dtype=torch.float32).contiguous()
+
+        with torch.no_grad():
+            pk = self._packed_params(dev)
+            layers: List[Tensor] = pk["layers"]
+            rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
+            ea = be.gather_rows(f32(edge_attr), perm) if A > 0 else None
+            node_feat, node_loc, node_vel = f32(node_feat), f32(node_loc), f32(node_vel)
+            attr = f32(node_attr) if Na > 0 else None
+            data_batch = data_batch.contiguous()
+
+            new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+            h, P, Q, Hn = new(N, H), new(N, H), new(N, H), new(N, H)
+            agg_m, agg_v = new(N, H), new(N, H)
+            x4, agg_x, trans_v = new(N, 4), new(N, 4), new(N, 4)
+            batch32 = new(N, dt=torch.int32)
+            vsum = torch.zeros(B, K, dtype=torch.float32, device=dev)
+            G = new(B, Cn, H)
+            Xv = f32(loc_mean).unsqueeze(-1).repeat(1, 1, Cn).contiguous()          # FastEGNN.py:300
+            Hv = pk["hv0"].unsqueeze(0).repeat(B, 1, 1).contiguous()                # FastEGNN.py:299 (as [B,C,64])
+            out = new(N, 3)
+            base = _lib.FLAG_NORMALIZE if self.normalize else 0
+            L = self.n_layers
+
+            be.embed((N, B, F, A, Cn, Na), node_feat, node_loc, data_batch, pk["emb_wt"], pk["emb_b"],
+                     layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
+            if L == 0:
+                return node_loc.clone(), Xv
+            self._sync_virtual(vsum)
+            be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
+            for i in range(L):
+                last = i == L - 1
+                flags = base | (_lib.FLAG_LAST if last else 0)
+                lp, lp_next = layers[i], (None if last else layers[i + 1])
+                agg_x.zero_()
+                vsum.zero_()
+                if not last:
+                    agg_m.zero_()
+                t0 = self._mark("edge")
+                be.edge_layer((N, E, A, Cn, Na), flags, row, col, ea, x4, P, Q, lp,
+                              None if last else agg_m, agg_x)
+                t1 = self._mark("edge_end")
+                be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp,
+                                 None if last else agg_v, trans_v, vsum)
+                t2 = self._mark("virtual_end")
+                be.node_layer((N, B, A, Cn, Na), flags, rowptr, batch32, h, x4, node_vel, attr,
+                              None if last else agg_m, agg_x, None if last else agg_v, trans_v, lp, lp_next,
+                              None if last else h, x4, None if last else P, None if last else Q,
+                              None if last else Hn, out if last else None, vsum)
+                t3 = self._mark("node_end")
+                if self._timing is not None:
+                    self._timing.append((i, t0[1], t1[1], t2[1], t3[1]))
+                self._sync_virtual(vsum)
+                be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vsum, Xv, Hv, lp, lp_next, G)
+        return out, Xv

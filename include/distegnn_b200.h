@@ -1,0 +1,210 @@
+/*
+ * distegnn_b200.h — C ABI of libdistegnn_b200.so: the sm_100a implementation of the DistEGNN hot
+ * path (FastEGNN per-layer equivariant message passing + the packed virtual-node statistics that are
+ * all-reduced across graph partitions).
+ *
+ * The reference (GLAD-RUC/DistEGNN) is pure Python/PyTorch and has no FFI of its own; the entry
+ * points below are what a binding for this path has to expose.  Each one cites the reference code it
+ * replaces (paths relative to the reference repo root).  The only caller in this repo is
+ * distegnn_b200/fast_egnn.py (ctypes); INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DISTEGNN_E* code; distegnn_last_error()
+ *     returns a thread-local human-readable message for the last failure;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer
+ *     (inputs, outputs, workspaces); the library never allocates, frees or synchronises;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); the call returns as soon as
+ *     the work is enqueued; it is safe inside CUDA-graph capture;
+ *   - fp32 everywhere, node ids int32 after distegnn_build_csr (int64 at the reference boundary);
+ *   - hidden width H is fixed at 64 (every shipped config: config/ *.yaml `hidden_nf: 64`).
+ *
+ * Internal data layout (all row-major, contiguous)
+ *   h      [N,64]   node features                x4     [N,4]  coordinates (xyz, w unused)
+ *   P,Q    [N,64]   first edge-MLP layer split per node: P = W1[:, 0:64]·h + b1, Q = W1[:,64:128]·h
+ *   Hn     [N,64]   first virtual-MLP layer node part:  W1v[:, 0:64]·h
+ *   Xv     [B,3,C]  virtual coordinates (reference layout)
+ *   Hv     [B,C,64] virtual features (reference layout is [B,64,C]; transposed once on the host)
+ *   G      [B,C,64] per-graph/channel constant of the first virtual-MLP layer:
+ *                   W1v[:,64:128]·Hv[b,:,c] + W1v[:,129:129+C]·m_X[b,:,c] + b1v
+ *   vsum   [B,K]    packed per-graph partial sums that are all-reduced (SUM) once per layer,
+ *                   K = 4 + 3C + 64C:  [0:3] Σ_i x_i   [3] node count   [4 : 4+3C] Σ_i ΔX_ic·φ_X as
+ *                   [3][C]   [4+3C : K] Σ_i mv_ic as [C][64]
+ */
+#ifndef DISTEGNN_B200_H
+#define DISTEGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISTEGNN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DISTEGNN_API __attribute__((visibility("default")))
+#else
+#define DISTEGNN_API
+#endif
+
+enum {
+    DISTEGNN_OK = 0,
+    DISTEGNN_EINVAL = -1,   /* bad argument (null pointer, unsupported size)              */
+    DISTEGNN_ECUDA = -2,    /* a CUDA runtime call or kernel launch failed                 */
+    DISTEGNN_EWORKSPACE = -3 /* caller-provided workspace too small                        */
+};
+
+/* limits of the compiled kernels */
+#define DISTEGNN_HIDDEN 64
+#define DISTEGNN_MAX_CHANNELS 16   /* virtual_channels C            */
+#define DISTEGNN_MAX_EDGE_ATTR 8   /* edge_attr_nf A                */
+#define DISTEGNN_MAX_NODE_ATTR 8   /* node_attr_nf Na               */
+#define DISTEGNN_MAX_NODE_FEAT 16  /* node_feat_nf F                */
+
+/* flags */
+#define DISTEGNN_FLAG_NORMALIZE 1u  /* E_GCL_vel(normalize=True), FastEGNN.py:242-244                  */
+#define DISTEGNN_FLAG_LAST 2u       /* last layer: h'/Hv' are dead (FastEGNN.py:307) — skip them        */
+#define DISTEGNN_FLAG_INIT 4u       /* virtual_update before layer 0: no X / Hv update, only x̄, m_X, G */
+
+DISTEGNN_API int distegnn_abi_version(void);
+DISTEGNN_API const char *distegnn_last_error(void);
+
+/* ---- per-layer parameter block -------------------------------------------------------------------
+ * One flat fp32 buffer per E_GCL_vel layer; every matrix is stored k-major ([in][out], i.e. the
+ * transpose of nn.Linear.weight) so a thread reads 4 consecutive outputs with one 16-byte load.
+ * Field order / source tensors (state_dict keys under gcl_<i>.):
+ */
+enum {
+    DISTEGNN_P_E_W1A = 0,  /* [64][64]  edge_mlp.0.weight[:, 0:64]^T   (h[row])            FastEGNN.py:69-74 */
+    DISTEGNN_P_E_W1B,      /* [64][64]  edge_mlp.0.weight[:, 64:128]^T (h[col])                              */
+    DISTEGNN_P_E_W1R,      /* [64]      edge_mlp.0.weight[:, 128]      (radial)                              */
+    DISTEGNN_P_E_W1E,      /* [A][64]   edge_mlp.0.weight[:, 129:129+A]^T (edge_attr)                        */
+    DISTEGNN_P_E_B1,       /* [64]      edge_mlp.0.bias                                                      */
+    DISTEGNN_P_E_W2,       /* [64][64]  edge_mlp.2.weight^T                                                  */
+    DISTEGNN_P_E_B2,       /* [64]                                                                            */
+    DISTEGNN_P_E_WC,       /* [64][64]  coord_mlp_r.0.weight^T                                 :96-110       */
+    DISTEGNN_P_E_BC,       /* [64]                                                                            */
+    DISTEGNN_P_E_W3,       /* [64]      coord_mlp_r.2.weight[0]                                               */
+    DISTEGNN_P_V_W1H,      /* [64][64]  edge_mlp_virtual.0.weight[:, 0:64]^T (h)                :76-81        */
+    DISTEGNN_P_V_W1V,      /* [64][64]  edge_mlp_virtual.0.weight[:, 64:128]^T (Hv)                           */
+    DISTEGNN_P_V_W1R,      /* [64]      edge_mlp_virtual.0.weight[:, 128] (‖ΔX‖)                              */
+    DISTEGNN_P_V_W1M,      /* [C][64]   edge_mlp_virtual.0.weight[:, 129:129+C]^T (m_X)                       */
+    DISTEGNN_P_V_B1,       /* [64]                                                                            */
+    DISTEGNN_P_V_W2,       /* [64][64]  edge_mlp_virtual.2.weight^T                                           */
+    DISTEGNN_P_V_B2,       /* [64]                                                                            */
+    DISTEGNN_P_V_WXV,      /* [64][64]  coord_mlp_r_virtual.0.weight^T                          :111          */
+    DISTEGNN_P_V_BXV,      /* [64]                                                                            */
+    DISTEGNN_P_V_W3XV,     /* [64]      coord_mlp_r_virtual.2.weight[0]                                       */
+    DISTEGNN_P_V_WX,       /* [64][64]  coord_mlp_v_virtual.0.weight^T                          :112          */
+    DISTEGNN_P_V_BX,       /* [64]                                                                            */
+    DISTEGNN_P_V_W3X,      /* [64]      coord_mlp_v_virtual.2.weight[0]                                       */
+    DISTEGNN_P_L_W,        /* [64][64]  coord_mlp_vel.0.weight^T                                :115-119      */
+    DISTEGNN_P_L_B,        /* [64]                                                                            */
+    DISTEGNN_P_L_W3,       /* [64]      coord_mlp_vel.2.weight[0]                                             */
+    DISTEGNN_P_L_B3,       /* [4]       coord_mlp_vel.2.bias (1 value, padded)                                */
+    DISTEGNN_P_N_W1,       /* [192+Na][64] node_mlp.0.weight^T  (h | agg | agg_v | node_attr)   :130-135      */
+    DISTEGNN_P_N_B1,       /* [64]                                                                            */
+    DISTEGNN_P_N_W2,       /* [64][64]  node_mlp.2.weight^T                                                   */
+    DISTEGNN_P_N_B2,       /* [64]                                                                            */
+    DISTEGNN_P_M_W1,       /* [128][64] node_mlp_virtual.0.weight^T (Hv | agg)                  :137-141      */
+    DISTEGNN_P_M_B1,       /* [64]                                                                            */
+    DISTEGNN_P_M_W2,       /* [64][64]  node_mlp_virtual.2.weight^T                                           */
+    DISTEGNN_P_M_B2,       /* [64]                                                                            */
+    DISTEGNN_P_NUM_FIELDS
+};
+
+/* Fills offsets_host[DISTEGNN_P_NUM_FIELDS] (in floats, each a multiple of 4) and *total_floats for a
+ * layer with edge_attr_nf=A, virtual_channels=C, node_attr_nf=Na.  Host-only, no CUDA call. */
+DISTEGNN_API int distegnn_param_layout(int A, int C, int Na, int64_t *offsets_host, int64_t *total_floats_host);
+
+/* ---- graph preprocessing (cached per edge_index by the caller) -----------------------------------
+ * Replaces the implicit "scatter by edge_index[0]" of unsorted_segment_sum/mean
+ * (models/FastEGNN.py:322-337, twins models/basic.py:50-66): the COO list [2,E] int64 (row =
+ * edge_index[0] = aggregation destination, col = edge_index[1] = neighbour; FastEGNN.py:238,250) is
+ * stably sorted by row into int32 CSR.  perm[e'] = original position of sorted edge e' (to permute
+ * edge_attr).  Self loops, duplicate edges and isolated nodes are legal (equivariant_test.py:26-27).
+ */
+DISTEGNN_API int distegnn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t *bytes_host);
+DISTEGNN_API int distegnn_build_csr(const int64_t *edge_index, int64_t n_nodes, int64_t n_edges,
+                       int32_t *rowptr /*[N+1]*/, int32_t *row /*[E]*/, int32_t *col /*[E]*/,
+                       int32_t *perm /*[E]*/, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* dst[i,:] = src[perm[i],:] for i < n_rows, rows of `width` floats (edge_attr into CSR order). */
+DISTEGNN_API int distegnn_gather_rows(const float *src, const int32_t *perm, int64_t n_rows, int width, float *dst,
+                         void *stream);
+
+/* ---- embedding + per-forward setup ---------------------------------------------------------------
+ * FastEGNN.forward prologue (FastEGNN.py:298-302): h0 = embedding_in(node_feat); also converts
+ * node_loc [N,3] → x4, data_batch int64 → batch32, computes P/Q/Hn of layer 0 from `layer0_params`,
+ * and accumulates Σx and the node count of every graph into vsum[:,0:4] (caller zeroes vsum).
+ * emb_wt is embedding_in.weight^T [F][64], emb_b [64].
+ */
+DISTEGNN_API int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
+                       const float *node_feat, const float *node_loc, const int64_t *data_batch,
+                       const float *emb_wt, const float *emb_b, const float *layer0_params,
+                       float *h, float *x4, int32_t *batch32, float *P, float *Q, float *Hn,
+                       float *vsum, void *stream);
+
+/* ---- real↔real edge stage ------------------------------------------------------------------------
+ * coord2radial + edge_model + the edge part of coord_model_vel + the edge part of node_model
+ * (FastEGNN.py:237-246, 144-150, 169-177, 206): for every CSR edge (i=row, j=col)
+ *   Δx = x_i − x_j, r = ‖Δx‖² (Δx /= sqrt(r)+1e-8 if NORMALIZE)
+ *   m  = SiLU(W2·SiLU(P_i + Q_j + w_r·r + W_e·a_ij) + b2),  φ = w3·SiLU(Wc·m + bc)
+ *   agg_m[i] += m   (skipped with FLAG_LAST),   agg_x[i].xyz += Δx·φ
+ * Sums, not means: the division by max(deg,1) happens in distegnn_node_layer_fwd.  The caller zeroes
+ * agg_m [N,64] and agg_x [N,4] before the call.
+ */
+DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+                            const int32_t *row, const int32_t *col, const float *edge_attr_sorted,
+                            const float *x4, const float *P, const float *Q,
+                            const float *layer_params, float *agg_m, float *agg_x, void *stream);
+
+/* ---- real↔virtual stage --------------------------------------------------------------------------
+ * Virtual geometry + edge_mode_virtual + the virtual parts of coord_model_vel, coord_model_virtual,
+ * node_model and node_model_virtual (FastEGNN.py:252-253, 154-163, 180, 191-193, 207, 220-223):
+ * for every node i (graph b) and channel c
+ *   ΔX = Xv[b,:,c] − x_i,  mv = SiLU(W2v·SiLU(Hn_i + G[b,c] + w_vr·‖ΔX‖) + b2v)
+ *   trans_v[i] = mean_c(−ΔX·φ_xv(mv)),  agg_v[i] = mean_c mv                       (per node)
+ *   vsum[b, 4:4+3C] += ΔX·φ_X(mv),      vsum[b, 4+3C:] += mv                       (per graph)
+ * With FLAG_LAST agg_v and the Σmv block are skipped.  Caller zeroes vsum.
+ */
+DISTEGNN_API int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                               const int32_t *batch32, const float *x4, const float *Hn,
+                               const float *Xv, const float *G, const float *layer_params,
+                               float *agg_v, float *trans_v /*[N,4]*/, float *vsum, void *stream);
+
+/* ---- node update ---------------------------------------------------------------------------------
+ * The rest of coord_model_vel and node_model (FastEGNN.py:177-183, 203-217):
+ *   x' = x + agg_x/max(deg,1) + trans_v + φ_v(h)·v
+ *   h' = h + W2n·SiLU(W1n·[h; agg_m/max(deg,1); agg_v; node_attr] + b1n) + b2n
+ * plus P/Q/Hn of the NEXT layer from next_layer_params, and vsum[b,0:4] += (x', 1).
+ * With FLAG_LAST only x' is produced and additionally written as [N,3] to node_loc_out (the model
+ * output); h_out/P/Q/Hn/next_layer_params may be null.  h_out may alias h, x4_out may alias x4.
+ */
+DISTEGNN_API int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                            const int32_t *rowptr, const int32_t *batch32, const float *h,
+                            const float *x4, const float *node_vel, const float *node_attr,
+                            const float *agg_m, const float *agg_x, const float *agg_v,
+                            const float *trans_v, const float *layer_params,
+                            const float *next_layer_params, float *h_out, float *x4_out, float *P,
+                            float *Q, float *Hn, float *node_loc_out, float *vsum, void *stream);
+
+/* ---- virtual-node update (after the all-reduce of vsum) ------------------------------------------
+ * The global halves of coord_model_virtual / node_model_virtual and the next layer's m_X
+ * (FastEGNN.py:199, 229-233, 258-264) from the *summed* statistics (weighted_average_reduce,
+ * FastEGNN.py:310-319, is Σ_r n_r·mean_r / Σ_r n_r = Σ_r sum_r / Σ_r n_r):
+ *   n = max(vsum[b,3],1);  Xv += vsum[b,4:4+3C]/n;  Hv += MLP_hv([Hv; vsum[b,4+3C:]/n])
+ *   x̄ = vsum[b,0:3]/n;  m_X = (Xv−x̄)ᵀ(Xv−x̄);  G_next = W1v_V·Hv + W1v_M·m_X + b1v (next layer's)
+ * FLAG_INIT: skip the Xv/Hv updates (before layer 0).  FLAG_LAST: only Xv is updated.
+ * layer_params: this layer's block (node_mlp_virtual); next_layer_params: the block whose virtual MLP
+ * consumes G (null with FLAG_LAST).  With FLAG_INIT pass layer 0's block as next_layer_params.
+ */
+DISTEGNN_API int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na, unsigned flags, const float *vsum,
+                                float *Xv, float *Hv, const float *layer_params,
+                                const float *next_layer_params, float *G, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTEGNN_B200_H */

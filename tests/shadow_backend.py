@@ -1,0 +1,145 @@
+"""Pure-torch stand-in for distegnn_b200.backend.CudaBackend — TEST INFRASTRUCTURE.
+
+It restates, stage by stage, what each C-ABI kernel computes (same decomposition: per-node P/Q/Hn
+split of the first MLP layers, SUMS instead of means, packed vsum buffer) so that
+  * the host-side orchestration in FastEGNN.forward (weight packing, flags, buffer reuse, the
+    one-all-reduce-per-layer protocol) can be checked against the oracle on a machine without a GPU,
+    including world_size=2 under gloo;
+  * on the GPU each kernel can be compared with its stage here in isolation.
+It is never imported by the package.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from distegnn_b200 import _lib
+
+H = 64
+
+
+def _fields(lp, A, C, Na):
+    offs, total = _lib.param_layout(A, C, Na)
+    sizes = dict(E_W1A=(H, H), E_W1B=(H, H), E_W1R=(H,), E_W1E=(A, H), E_B1=(H,), E_W2=(H, H), E_B2=(H,),
+                 E_WC=(H, H), E_BC=(H,), E_W3=(H,), V_W1H=(H, H), V_W1V=(H, H), V_W1R=(H,), V_W1M=(C, H),
+                 V_B1=(H,), V_W2=(H, H), V_B2=(H,), V_WXV=(H, H), V_BXV=(H,), V_W3XV=(H,), V_WX=(H, H),
+                 V_BX=(H,), V_W3X=(H,), L_W=(H, H), L_B=(H,), L_W3=(H,), L_B3=(1,), N_W1=(3 * H + Na, H),
+                 N_B1=(H,), N_W2=(H, H), N_B2=(H,), M_W1=(2 * H, H), M_B1=(H,), M_W2=(H, H), M_B2=(H,))
+    out = {}
+    for k, shp in sizes.items():
+        n = 1
+        for s in shp:
+            n *= s
+        out[k] = lp[offs[k]:offs[k] + n].reshape(shp)
+    return out
+
+
+class ShadowBackend:
+    name = "torch-shadow (tests only)"
+
+    def __init__(self):
+        self.launches = 0
+
+    def build_csr(self, edge_index, n_nodes):
+        row64 = edge_index[0]
+        perm = torch.argsort(row64, stable=True)
+        row = row64[perm].to(torch.int32)
+        col = edge_index[1][perm].to(torch.int32)
+        counts = torch.bincount(row64, minlength=n_nodes)
+        rowptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=edge_index.device)
+        rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        return rowptr, row, col, perm.to(torch.int32)
+
+    def gather_rows(self, src, perm):
+        return src[perm.long()].contiguous()
+
+    def embed(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
+              Hn, vsum):
+        N, B, Fn, A, C, Na = dims
+        h.copy_(node_feat @ emb_wt + emb_b)
+        x4.zero_()
+        x4[:, :3] = node_loc
+        batch32.copy_(data_batch.to(torch.int32))
+        f = _fields(layer0, A, C, Na)
+        P.copy_(h @ f["E_W1A"] + f["E_B1"])
+        Q.copy_(h @ f["E_W1B"])
+        Hn.copy_(h @ f["V_W1H"])
+        vsum[:, 0:3].index_add_(0, data_batch, node_loc)
+        vsum[:, 3].index_add_(0, data_batch, torch.ones(N, dtype=vsum.dtype, device=vsum.device))
+
+    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x):
+        N, E, A, C, Na = dims
+        if E == 0:
+            return
+        f = _fields(lp, A, C, Na)
+        r, c = row.long(), col.long()
+        dx = x4[r, :3] - x4[c, :3]
+        radial = (dx ** 2).sum(1, keepdim=True)
+        if flags & _lib.FLAG_NORMALIZE:
+            dx = dx / (radial.sqrt() + 1e-8)
+        pre = P[r] + Q[c] + radial * f["E_W1R"]
+        if A:
+            pre = pre + ea @ f["E_W1E"]
+        m = F.silu(F.silu(pre) @ f["E_W2"] + f["E_B2"])
+        phi = F.silu(m @ f["E_WC"] + f["E_BC"]) @ f["E_W3"]
+        if not flags & _lib.FLAG_LAST:
+            agg_m.index_add_(0, r, m)
+        agg_x[:, :3].index_add_(0, r, dx * phi.unsqueeze(1))
+
+    def virtual_layer(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum):
+        N, B, A, C, Na = dims
+        f = _fields(lp, A, C, Na)
+        b = batch32.long()
+        dX = Xv[b] - x4[:, :3].unsqueeze(-1)                       # [N,3,C]
+        vr = dX.norm(dim=1)                                        # [N,C]
+        pre = Hn.unsqueeze(1) + G[b] + vr.unsqueeze(-1) * f["V_W1R"]   # [N,C,64]
+        mv = F.silu(F.silu(pre) @ f["V_W2"] + f["V_B2"])           # [N,C,64]
+        phi_xv = F.silu(mv @ f["V_WXV"] + f["V_BXV"]) @ f["V_W3XV"]    # [N,C]
+        phi_x = F.silu(mv @ f["V_WX"] + f["V_BX"]) @ f["V_W3X"]
+        trans_v.zero_()
+        trans_v[:, :3] = (-dX * phi_xv.unsqueeze(1)).mean(-1)
+        vsum[:, 4:4 + 3 * C].index_add_(0, b, (dX * phi_x.unsqueeze(1)).reshape(N, 3 * C))
+        if not flags & _lib.FLAG_LAST:
+            agg_v.copy_(mv.mean(1))
+            vsum[:, 4 + 3 * C:].index_add_(0, b, mv.reshape(N, C * H))
+
+    def node_layer(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
+                   lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum):
+        N, B, A, C, Na = dims
+        f = _fields(lp, A, C, Na)
+        b = batch32.long()
+        deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(h.dtype).unsqueeze(1)
+        phiv = F.silu(h @ f["L_W"] + f["L_B"]) @ f["L_W3"] + f["L_B3"]
+        xn = x4[:, :3] + agg_x[:, :3] / deg + trans_v[:, :3] + phiv.unsqueeze(1) * vel
+        if not flags & _lib.FLAG_LAST:
+            cat = [h, agg_m / deg, agg_v] + ([attr] if Na else [])
+            hn = h + F.silu(torch.cat(cat, 1) @ f["N_W1"] + f["N_B1"]) @ f["N_W2"] + f["N_B2"]
+            g = _fields(lp_next, A, C, Na)
+            P.copy_(hn @ g["E_W1A"] + g["E_B1"])
+            Q.copy_(hn @ g["E_W1B"])
+            Hn.copy_(hn @ g["V_W1H"])
+            h_out.copy_(hn)
+        x4_out[:, :3] = xn
+        if loc_out is not None:
+            loc_out.copy_(xn)
+        vsum[:, 0:3].index_add_(0, b, xn)
+        vsum[:, 3].index_add_(0, b, torch.ones(N, dtype=vsum.dtype, device=vsum.device))
+
+    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G):
+        B, A, C, Na = dims
+        init, last = bool(flags & _lib.FLAG_INIT), bool(flags & _lib.FLAG_LAST)
+        n = vsum[:, 3].clamp(min=1)
+        if not init:
+            Xv += vsum[:, 4:4 + 3 * C].reshape(B, 3, C) / n.view(B, 1, 1)
+        if last:
+            return
+        if not init:
+            f = _fields(lp, A, C, Na)
+            agg = vsum[:, 4 + 3 * C:].reshape(B, C, H) / n.view(B, 1, 1)
+            Hv += F.silu(torch.cat([Hv, agg], -1) @ f["M_W1"] + f["M_B1"]) @ f["M_W2"] + f["M_B2"]
+        g = _fields(lp_next, A, C, Na)
+        xbar = vsum[:, 0:3] / n.view(B, 1)
+        Z = Xv - xbar.unsqueeze(-1)                                # [B,3,C]
+        mX = torch.einsum("bdi,bdj->bij", Z, Z)                    # [B,C,C]
+        # G[b,c,:] = Hv[b,c,:]·W1v_V + Σ_j m_X[b,j,c]·W1v_M[j,:] + b1v
+        G.copy_(Hv @ g["V_W1V"] + torch.einsum("bjc,jn->bcn", mX, g["V_W1M"]) + g["V_B1"])

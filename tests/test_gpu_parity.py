@@ -1,0 +1,280 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against
+  * the reference-generated golden fixtures,
+  * the oracle on seeded inputs,
+  * each kernel's torch restatement (tests/shadow_backend.py) in isolation,
+  * size-independent properties at larger sizes (SE(3) equivariance, edge-order invariance,
+    partition/block-diagonal equivalence).
+Tolerances (fp32 path): |out − ref64| ≤ 1e-5·max(1,|out|), relative displacement error
+≤ 1e-4, equivariance residual ≤ 1e-4 (the reference's own gate, equivariant_test.py:62).
+"""
+import numpy as np
+import pytest
+import torch
+
+from distegnn_b200 import FastEGNN, _lib, synth
+from oracle import fastegnn_oracle as orc
+from tests.helpers import SINGLE_CASES, golden_inputs, golden_trace, load_golden, max_abs, rel_disp_err
+from tests.shadow_backend import ShadowBackend
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL = 1e-5
+REL_DISP_TOL = 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no fallback)"
+    return torch.device("cuda:0")
+
+
+def to_dev(inp):
+    return {k: (v.to(dev()) if v is not None else None) for k, v in inp.items()}
+
+
+def cuda_model(kw, sd, world_size=1):
+    m = FastEGNN(hidden_nf=64, world_size=world_size, **kw)
+    m.load_state_dict(sd)
+    return m.to(dev()).eval()
+
+
+def oracle64(sd, inp, normalize):
+    sd64 = {k: v.double() for k, v in sd.items()}
+    i64 = {k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in inp.items()}
+    return orc.forward(sd64, **i64, normalize=normalize)
+
+
+def check_close(out, X, ref, refX, pos, what=""):
+    out, X = out.cpu(), X.cpu()
+    e_abs, scale = max_abs(out, ref), max(1.0, float(ref.abs().max()))
+    e_rel = rel_disp_err(out, ref, pos)
+    e_X = max_abs(X, refX)
+    msg = f"{what}: abs {e_abs:.3e} (scale {scale:.2f}) rel-disp {e_rel:.3e} virtual {e_X:.3e}"
+    print(msg)
+    assert e_abs <= ABS_TOL * scale, msg
+    assert e_rel <= REL_DISP_TOL, msg
+    assert e_X <= ABS_TOL * max(1.0, float(refX.abs().max())), msg
+
+
+def test_library_loaded_and_abi():
+    lib = _lib.load()
+    assert lib.distegnn_abi_version() == 1
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_golden_fixtures(name):
+    z, kw, sd = load_golden(name)
+    inp = golden_inputs(z)
+    m = cuda_model(kw, sd)
+    with torch.no_grad():
+        out, X = m(**to_dev(inp))
+    check_close(out, X, torch.from_numpy(z["out64.node_loc"]), torch.from_numpy(z["out64.virtual_loc"]),
+                inp["node_loc"], name)
+
+
+def _stage_inputs(kw, sd, inp):
+    """Run the torch stand-in on the GPU to get every intermediate buffer of layer 0."""
+    m = cuda_model(kw, sd)
+    m._backend = ShadowBackend()
+    return m
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_per_layer_trace_against_reference(name):
+    """h / x after every layer, not just the final coordinates (parity is deceptively easy at init)."""
+    z, kw, sd = load_golden(name)
+    inp = golden_inputs(z)
+    ref_h, ref_x = golden_trace(z, "h"), golden_trace(z, "x")
+    for L in range(1, kw["n_layers"] + 1):
+        # a model truncated to L layers: its last layer must reproduce x_L; use L+1 layers to read h_L
+        sub = {k: v for k, v in sd.items() if not k.startswith("gcl_") or int(k.split(".")[0][4:]) < L}
+        kwL = dict(kw, n_layers=L)
+        m = cuda_model(kwL, sub)
+        with torch.no_grad():
+            out, _ = m(**to_dev(inp))
+        e = max_abs(out.cpu(), ref_x[L - 1])
+        print(f"{name} layer {L}: x err {e:.3e}")
+        assert e <= 2e-5 * max(1.0, float(ref_x[L - 1].abs().max()))
+
+
+def _kernel_vs_shadow(name):
+    z, kw, sd = load_golden(name)
+    inp = to_dev(golden_inputs(z))
+    return z, kw, sd, inp
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_each_kernel_against_torch_restatement(name):
+    """Drive both backends through layer 0 with identical inputs and compare every output buffer."""
+    from distegnn_b200.backend import cuda_backend
+    z, kw, sd, inp = _kernel_vs_shadow(name)
+    m = cuda_model(kw, sd)
+    pk = m._packed_params(dev())
+    A, C, Na, F = kw["edge_attr_nf"], kw["virtual_channels"], kw["node_attr_nf"], kw["node_feat_nf"]
+    N, E, B = inp["node_loc"].shape[0], inp["edge_index"].shape[1], inp["loc_mean"].shape[0]
+    K = 4 + 3 * C + 64 * C
+    res = {}
+    for tag, be in (("cuda", cuda_backend()), ("ref", ShadowBackend())):
+        new = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev())
+        h, P, Q, Hn, agg_m, agg_v = (new(N, 64) for _ in range(6))
+        x4, agg_x, trans_v = new(N, 4), new(N, 4), new(N, 4)
+        b32, vsum, G = new(N, dt=torch.int32), new(B, K), new(B, C, 64)
+        Xv = inp["loc_mean"].unsqueeze(-1).repeat(1, 1, C).contiguous()
+        Hv = pk["hv0"].unsqueeze(0).repeat(B, 1, 1).contiguous()
+        rowptr, row, col, perm = be.build_csr(inp["edge_index"].contiguous(), N)
+        ea = be.gather_rows(inp["edge_attr"], perm)
+        be.embed((N, B, F, A, C, Na), inp["node_feat"], inp["node_loc"], inp["data_batch"], pk["emb_wt"],
+                 pk["emb_b"], pk["layers"][0], h, x4, b32, P, Q, Hn, vsum)
+        vs0 = vsum.clone()
+        be.virtual_update((B, A, C, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, pk["layers"][0], G)
+        G0 = G.clone()
+        vsum.zero_()
+        flags = _lib.FLAG_NORMALIZE if kw["normalize"] else 0
+        be.edge_layer((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, pk["layers"][0], agg_m, agg_x)
+        be.virtual_layer((N, B, A, C, Na), flags, b32, x4, Hn, Xv, G, pk["layers"][0], agg_v, trans_v, vsum)
+        vs1 = vsum.clone()
+        h2, x42, P2, Q2, Hn2 = new(N, 64), new(N, 4), new(N, 64), new(N, 64), new(N, 64)
+        be.node_layer((N, B, A, C, Na), flags, rowptr, b32, h, x4, inp["node_vel"], inp["node_attr"], agg_m,
+                      agg_x, agg_v, trans_v, pk["layers"][0], pk["layers"][1], h2, x42, P2, Q2, Hn2, None,
+                      vsum)
+        vs2 = vsum.clone()
+        be.virtual_update((B, A, C, Na), 0, vsum, Xv, Hv, pk["layers"][0], pk["layers"][1], G)
+        torch.cuda.synchronize()
+        res[tag] = dict(rowptr=rowptr, row=row, col=col, ea=ea, h=h, x4=x4[:, :3], b32=b32, P=P, Q=Q, Hn=Hn,
+                        vs0=vs0[:, :4], G0=G0, agg_m=agg_m, agg_x=agg_x[:, :3], agg_v=agg_v,
+                        trans_v=trans_v[:, :3], vs1=vs1[:, 4:], h2=h2, x42=x42[:, :3], P2=P2, Q2=Q2, Hn2=Hn2,
+                        vs2=vs2[:, :4], Xv=Xv, Hv=Hv, G1=G)
+    bad = []
+    for k in res["ref"]:
+        a, b = res["cuda"][k], res["ref"][k]
+        if a.dtype in (torch.int32, torch.int64):
+            if k in ("rowptr", "row", "b32"):
+                ok = torch.equal(a, b)
+            else:   # col: same multiset per row (stable sort makes it identical)
+                ok = torch.equal(a, b)
+            err = 0.0 if ok else 1.0
+        else:
+            scale = max(1e-6, float(b.abs().max()))
+            err = max_abs(a, b) / scale
+            ok = err <= 2e-5
+        print(f"{name:24s} {k:8s} rel err {err:.3e}")
+        if not ok:
+            bad.append((k, err))
+    assert not bad, bad
+
+
+def _rotation(seed):
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return torch.from_numpy(q.astype(np.float32))
+
+
+def test_equivariance_reference_script_on_gpu():
+    """equivariant_test.py restated (10 nodes, 20 random edges incl. self loops/duplicates, F=1, A=1,
+    C=3, 4 layers, atol 1e-4) — several seeds, through the CUDA path."""
+    for seed in range(5):
+        torch.manual_seed(seed)
+        m = FastEGNN(node_feat_nf=1, node_attr_nf=0, edge_attr_nf=1, hidden_nf=64, virtual_channels=3,
+                     world_size=1, n_layers=4).to(dev())
+        g = torch.Generator().manual_seed(100 + seed)
+        n, e = 10, 20
+        x, v = torch.rand(n, 3, generator=g) * 10, torch.rand(n, 3, generator=g) * 10
+        f = torch.rand(n, 1, generator=g) * 10
+        ei = torch.randint(0, 10, (2, e), generator=g)
+        ea = torch.rand(e, 1, generator=g) * 10
+        b = torch.zeros(n, dtype=torch.long)
+        R, t = _rotation(seed), torch.randn(3, generator=g) * 5
+        d = dev()
+        with torch.no_grad():
+            out, _ = m(f.to(d), x.to(d), v.to(d), x.mean(0, keepdim=True).to(d), ei.to(d), b.to(d), ea.to(d))
+            xr = x @ R + t
+            out_r, _ = m(f.to(d), xr.to(d), (v @ R).to(d), xr.mean(0, keepdim=True).to(d), ei.to(d), b.to(d),
+                         ea.to(d))
+        assert torch.allclose(out.cpu() @ R + t, out_r.cpu(), atol=1e-4)
+
+
+@pytest.mark.parametrize("wname,n,coord_gain", [("water3d_10k", 10_000, 0.05), ("fluid113k", 30_000, 0.05),
+                                                ("nbody100", 100, 0.001)])
+def test_workloads_against_oracle(wname, n, coord_gain):
+    """BASELINE.json configs at sizes the fp64 oracle finishes in seconds, trained-like coord heads."""
+    w = synth.WORKLOADS[wname]
+    inp = synth.make_partitions(w, n_nodes=n, seed=3)[0]
+    sd = orc.init_state_dict(w.node_feat_nf, w.node_attr_nf, w.edge_attr_nf, 64, w.virtual_channels, 4,
+                             seed=4, coord_gain=coord_gain)
+    kw = dict(node_feat_nf=w.node_feat_nf, node_attr_nf=w.node_attr_nf, edge_attr_nf=w.edge_attr_nf,
+              virtual_channels=w.virtual_channels, n_layers=4, normalize=w.normalize)
+    m = cuda_model(kw, sd)
+    with torch.no_grad():
+        out, X = m(**to_dev(inp))
+    ref, refX = oracle64(sd, inp, w.normalize)
+    check_close(out, X, ref, refX, inp["node_loc"], wname)
+
+
+def test_batched_graphs_against_oracle():
+    """N-body style batch: 40 graphs x 100 nodes fully connected (tiles straddle graph boundaries)."""
+    w = synth.WORKLOADS["nbody100"]
+    parts = [synth.make_partitions(w, seed=s)[0] for s in range(40)]
+    n = 100
+    cat = lambda k: torch.cat([p[k] for p in parts])
+    inp = dict(node_feat=cat("node_feat"), node_loc=cat("node_loc"), node_vel=cat("node_vel"),
+               loc_mean=cat("loc_mean"),
+               edge_index=torch.cat([p["edge_index"] + i * n for i, p in enumerate(parts)], 1),
+               data_batch=torch.arange(40).repeat_interleave(n), edge_attr=cat("edge_attr"), node_attr=None)
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 4, seed=9, coord_gain=0.01)
+    kw = dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=4, normalize=True)
+    m = cuda_model(kw, sd)
+    with torch.no_grad():
+        out, X = m(**to_dev(inp))
+    ref, refX = oracle64(sd, inp, True)
+    check_close(out, X, ref, refX, inp["node_loc"], "nbody batch 40")
+
+
+def test_edge_cases():
+    d = dev()
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 2, seed=1, coord_gain=0.1)
+    kw = dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=2)
+    m = cuda_model(kw, sd)
+    g = torch.Generator().manual_seed(0)
+    for n, ei in [(7, torch.zeros(2, 0, dtype=torch.long)),                       # no edges at all
+                  (1, torch.zeros(2, 3, dtype=torch.long)),                       # single node, self loops
+                  (300, torch.stack([torch.zeros(299, dtype=torch.long), torch.arange(1, 300)])),  # star: deg 299
+                  (129, torch.randint(0, 129, (2, 128 * 3 + 1), generator=g))]:  # ragged last tile
+        inp = dict(node_feat=torch.randn(n, 2, generator=g), node_loc=torch.randn(n, 3, generator=g),
+                   node_vel=torch.randn(n, 3, generator=g), loc_mean=torch.zeros(1, 3), edge_index=ei,
+                   data_batch=torch.zeros(n, dtype=torch.long),
+                   edge_attr=torch.rand(ei.shape[1], 2, generator=g), node_attr=None)
+        with torch.no_grad():
+            out, X = m(**to_dev(inp))
+        ref, refX = oracle64(sd, inp, False)
+        check_close(out, X, ref, refX, inp["node_loc"], f"edge case n={n} e={ei.shape[1]}")
+    with pytest.raises(ValueError):
+        m(torch.zeros(4, 3, device=d), torch.zeros(4, 3, device=d), torch.zeros(4, 3, device=d),
+          torch.zeros(1, 3, device=d), torch.zeros(2, 0, dtype=torch.long, device=d),
+          torch.zeros(4, dtype=torch.long, device=d), torch.zeros(0, 2, device=d))
+
+
+def test_large_graph_properties():
+    """config-5-like density at 200k nodes (≈4M edges): SE(3) equivariance, invariance to a random
+    permutation of the edge list, and agreement with the fp32 oracle (one forward on host cores)."""
+    w = synth.WORKLOADS["synth1m"]
+    inp = synth.make_partitions(w, n_nodes=200_000, seed=0)[0]
+    sd = orc.init_state_dict(3, 2, 2, 64, 8, 4, seed=2, coord_gain=0.05)
+    kw = dict(node_feat_nf=3, node_attr_nf=2, edge_attr_nf=2, virtual_channels=8, n_layers=4)
+    m = cuda_model(kw, sd)
+    di = to_dev(inp)
+    with torch.no_grad():
+        out, X = m(**di)
+        perm = torch.randperm(inp["edge_index"].shape[1], generator=torch.Generator().manual_seed(1)).to(dev())
+        out_p, X_p = m(**{**di, "edge_index": di["edge_index"][:, perm].contiguous(),
+                          "edge_attr": di["edge_attr"][perm].contiguous()})
+        R, t = _rotation(5).to(dev()), torch.tensor([0.3, -1.0, 2.0], device=dev())
+        xr = di["node_loc"] @ R + t
+        out_r, _ = m(**{**di, "node_loc": xr, "node_vel": di["node_vel"] @ R,
+                        "loc_mean": di["loc_mean"] @ R + t})
+    scale = float(out.abs().max())
+    assert max_abs(out, out_p) <= 2e-6 * max(1.0, scale)
+    assert max_abs(X, X_p) <= 2e-6 * max(1.0, scale)
+    assert max_abs(out @ R + t, out_r) <= 1e-4
+    ref, refX = orc.forward(sd, **inp)
+    check_close(out, X, ref, refX, inp["node_loc"], "synth 200k")
