@@ -74,6 +74,13 @@ class CudaBackend:
                                                self._s(x4)), "edge_layer_fwd")
         self.launches += 1 if E else 0
 
+    def edge_layer_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
+        """fp32-FMA twin of edge_layer (cross-check only; FastEGNN.forward never calls it)."""
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_fwd_simt(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
+                                                    ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
+                                                    ptr(agg_x), self._s(x4)), "edge_layer_fwd_simt")
+
     def virtual_layer(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
         N, B, A, Cn, Na = dims
         check(self.lib.distegnn_virtual_layer_fwd(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),

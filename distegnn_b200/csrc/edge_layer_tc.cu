@@ -1,0 +1,377 @@
+// Real<->real edge stage on the 5th-gen tensor cores (tcgen05 + TMEM), the production edge kernel.
+// Same math and outputs as edge_layer.cu (the fp32-FMA version kept as distegnn_edge_layer_fwd_simt for
+// cross-checks); replaces reference models/FastEGNN.py:237-246,144-150,169-177,206 and the scatter_add_ of
+// :322-337.
+//
+// One CTA per SM, 256 threads = 2 independent warpgroups (WG).  A WG owns one 128-edge tile at a time;
+// thread r of the WG owns edge r of the tile end to end (TMEM lane r):
+//   stage 0  the 256-byte neighbour rows Q[col] of the NEXT tile are fetched by the TMA engine
+//            (cp.async.bulk global->shared, one copy per edge, completion on an mbarrier) while the
+//            current tile computes — the [E,64] gathers of the reference never exist;
+//   stage 1  a1 = SiLU(P[row] + Q[col] + w_r·r + W_e·a)  -> split hi/lo (3xTF32) -> tcgen05.st to TMEM;
+//   MMA 1    D = a1·W2ᵀ : 24 tcgen05.mma (M128,N64,K8, kind::tf32; lo·hi + hi·lo + hi·hi) issued by one
+//            thread, B = W2 resident in shared memory (no-swizzle K-major descriptor), D in TMEM;
+//   stage 2  m = SiLU(D + b2) (tcgen05.ld, row per thread) -> m row to shared (for the segment sum) and
+//            hi/lo back to TMEM;
+//   MMA 2    D = m·Wcᵀ ; while it runs the WG segment-sums m over runs of equal destination row
+//            (column walk over the shared tile, RED.ADD per (run, column));
+//   stage 3  φ = w3·SiLU(D + bc), Δx·φ reduced over runs of equal row with warp shuffles, RED.ADD to agg_x.
+// While one WG waits on its MMAs the other WG's SIMT stages use the issue slots, and vice versa.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace degnn {
+
+struct EdgeTcArgs {
+    int64_t N, E;
+    int A;
+    unsigned flags;
+    const int32_t* row;
+    const int32_t* col;
+    const float* ea;
+    const float* x4;
+    const float* P;
+    const float* Q;
+    const float* w1r;
+    const float* w1e;
+    const float* w2;   // k-major [k][n]
+    const float* b2;
+    const float* wc;   // k-major [k][n]
+    const float* bc;
+    const float* w3;
+    float* agg_m;
+    float* agg_x;
+};
+
+constexpr int TC_THREADS = 256;
+constexpr int QROW = 68;                                  // floats per staged row (272 B: 16B-aligned, bank-shifted)
+constexpr int QBUF_FLOATS = TILE_M * QROW;                // 8704
+constexpr int TC_SMEM_BYTES = 4 * 16384                   // W2 hi/lo, Wc hi/lo (UMMA canonical layout)
+                              + 2 * 2 * QBUF_FLOATS * 4   // 2 WGs x 2 staging buffers
+                              + (4 * H + DISTEGNN_MAX_EDGE_ATTR * H) * 4   // b2, bc, w3, w1r, w1e
+                              + 2 * 2 * TILE_M * 4        // srow per WG, double-buffered by tile parity
+                              + 64;                       // mbarriers + tmem base
+
+__device__ __forceinline__ void stage_weight_umma(float* hi, float* lo, const float* __restrict__ wt_kmajor,
+                                                  int tid, int nthreads) {
+    // wt_kmajor[k*64+n] = W[n][k]; B operand wants element (n,k) at b_elem_offset(n,k)
+    for (int i = tid; i < H * H; i += nthreads) {
+        const int k = i >> 6, n = i & 63;
+        uint32_t h, l;
+        umma::split_tf32(__ldg(wt_kmajor + i), h, l);
+        const uint32_t o = umma::b_elem_offset(n, k);
+        hi[o] = __uint_as_float(h);
+        lo[o] = __uint_as_float(l);
+    }
+}
+
+// 24 MMAs: D = Alo·Bhiᵀ + Ahi·Bloᵀ + Ahi·Bhiᵀ  (small terms first), then commit to `bar`
+__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi,
+                                                  uint64_t b_lo, uint32_t idesc, uint64_t* bar) {
+    constexpr uint64_t KSTEP = (2 * umma::B_LBO) >> 4;   // descriptor start-address units per K=8 step
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) umma::mma_tf32_ts(d, a_lo + 8 * ks, b_hi + ks * KSTEP, idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) umma::mma_tf32_ts(d, a_hi + 8 * ks, b_lo + ks * KSTEP, idesc, 1);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) umma::mma_tf32_ts(d, a_hi + 8 * ks, b_hi + ks * KSTEP, idesc, 1);
+    umma::mma_commit(bar);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const EdgeTcArgs a) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* W2hi = reinterpret_cast<float*>(smem_raw);
+    float* W2lo = W2hi + 4096;
+    float* Wchi = W2lo + 4096;
+    float* Wclo = Wchi + 4096;
+    float* qbufs = Wclo + 4096;                               // [2 WG][2][QBUF_FLOATS]
+    float* b2s = qbufs + 4 * QBUF_FLOATS;
+    float* bcs = b2s + H;
+    float* w3s = bcs + H;
+    float* w1rs = w3s + H;
+    float* w1es = w1rs + H;                                   // [A][64]
+    int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);   // [2 WG][2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(srow_all + 4 * TILE_M);         // [2 WG][3]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int tid = threadIdx.x;
+    const int wg = tid >> 7;               // warpgroup 0/1
+    const int t = tid & 127;               // row owned inside the tile
+    const int lane = tid & 31;
+    const int wq = (tid >> 5) & 3;         // warp index inside the WG == TMEM lane quarter
+    const int A = a.A;
+    const bool normalize = a.flags & DISTEGNN_FLAG_NORMALIZE;
+    const bool need_m = !(a.flags & DISTEGNN_FLAG_LAST);
+
+    // ---- one-time setup -------------------------------------------------------------------------
+    stage_weight_umma(W2hi, W2lo, a.w2, tid, TC_THREADS);
+    stage_weight_umma(Wchi, Wclo, a.wc, tid, TC_THREADS);
+    if (tid < H) {
+        b2s[tid] = a.b2[tid];
+        bcs[tid] = a.bc[tid];
+        w3s[tid] = a.w3[tid];
+        w1rs[tid] = a.w1r[tid];
+    }
+    for (int i = tid; i < A * H; i += TC_THREADS) w1es[i] = a.w1e[i];
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if ((tid >> 5) == 0) tmem_alloc(tmem_base_s, 512);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    const uint32_t tbase = *tmem_base_s;
+    const uint32_t col0 = tbase + (uint32_t)wg * 256u;             // this WG's TMEM columns
+    const uint32_t tA_hi = col0, tA_lo = col0 + 64, tD = col0 + 128;
+    const uint32_t lane_off = ((uint32_t)(32 * wq)) << 16;          // this warp's TMEM lane quarter
+    const uint32_t idesc = make_idesc_tf32(128, 64);
+    const uint64_t dW2hi = make_b_desc(smem_u32(W2hi), B_LBO, B_SBO), dW2lo = make_b_desc(smem_u32(W2lo), B_LBO, B_SBO);
+    const uint64_t dWchi = make_b_desc(smem_u32(Wchi), B_LBO, B_SBO), dWclo = make_b_desc(smem_u32(Wclo), B_LBO, B_SBO);
+    float* qbuf[2] = {qbufs + (wg * 2 + 0) * QBUF_FLOATS, qbufs + (wg * 2 + 1) * QBUF_FLOATS};
+    int* srow2 = srow_all + wg * 2 * TILE_M;
+    uint64_t* qbar = bars + wg * 3;        // [2]
+    uint64_t* mbar = bars + wg * 3 + 2;
+    const uint32_t bar_id = 1 + wg;
+
+    const int64_t num_tiles = (a.E + TILE_M - 1) / TILE_M;
+    const int64_t stride = (int64_t)gridDim.x * 2;
+    int64_t tile = (int64_t)blockIdx.x * 2 + wg;
+
+    // metadata of the tile about to be processed (registers) and of the prefetched one
+    int row_c = -1, col_c = 0;
+    float ea_c[DISTEGNN_MAX_EDGE_ATTR];
+    auto load_meta = [&](int64_t tl, int& r, int& c, float (&ea)[DISTEGNN_MAX_EDGE_ATTR]) {
+        const int64_t e = tl * TILE_M + t;
+        r = -1;
+        c = 0;
+        if (tl < num_tiles && e < a.E) {
+            r = __ldg(a.row + e);
+            c = __ldg(a.col + e);
+#pragma unroll
+            for (int k = 0; k < DISTEGNN_MAX_EDGE_ATTR; ++k)
+                if (k < A) ea[k] = __ldg(a.ea + e * A + k);
+        }
+    };
+    auto prefetch_q = [&](int64_t tl, int r, int c, float* dst, uint64_t* bar) {
+        if (tl < num_tiles) {
+            if (t == 0) {
+                const int64_t nvalid = min((int64_t)TILE_M, a.E - tl * TILE_M);
+                mbar_expect_tx(bar, (uint32_t)nvalid * (H * 4));
+            }
+            if (r >= 0) bulk_g2s(dst + t * QROW, a.Q + (size_t)c * H, H * 4, bar);
+        }
+    };
+
+    if (tile < num_tiles) {
+        load_meta(tile, row_c, col_c, ea_c);
+        prefetch_q(tile, row_c, col_c, qbuf[0], &qbar[0]);
+    }
+
+    for (int it = 0; tile < num_tiles; ++it, tile += stride) {
+        const int b = it & 1;
+        float* qb = qbuf[b];
+        int* srow = srow2 + b * TILE_M;   // read by this tile's segment sum until the next-but-one tile
+        const bool valid = row_c >= 0;
+
+        // ---- stage 1 ---------------------------------------------------------------------------
+        float dx = 0.f, dy = 0.f, dz = 0.f, radial = 0.f;
+        if (valid) {
+            const float4 xi = ldg4(a.x4 + (size_t)row_c * 4), xj = ldg4(a.x4 + (size_t)col_c * 4);
+            dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
+            radial = dx * dx + dy * dy + dz * dz;
+            if (normalize) {
+                const float inv = 1.0f / (sqrtf(radial) + 1e-8f);
+                dx *= inv; dy *= inv; dz *= inv;
+            }
+        }
+        mbar_wait(&qbar[b], (uint32_t)((it >> 1) & 1));
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t hi[16], lo[16];
+            if (valid) {
+                const float* prow = a.P + (size_t)row_c * H + 16 * c;
+                const float* qrow = qb + t * QROW + 16 * c;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 p = ldg4(prow + 4 * j4);
+                    const float4 q = *reinterpret_cast<const float4*>(qrow + 4 * j4);
+                    float4 pre = fma4(radial, *reinterpret_cast<const float4*>(w1rs + 16 * c + 4 * j4), add4(p, q));
+#pragma unroll
+                    for (int k = 0; k < DISTEGNN_MAX_EDGE_ATTR; ++k)
+                        if (k < A)
+                            pre = fma4(ea_c[k], *reinterpret_cast<const float4*>(w1es + k * H + 16 * c + 4 * j4), pre);
+                    pre = silu4(pre);
+                    split_tf32(pre.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
+                    split_tf32(pre.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
+                    split_tf32(pre.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
+                    split_tf32(pre.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0u;
+            }
+            __syncwarp();
+            tmem_st16(lane_off + tA_hi + 16 * c, hi);
+            tmem_st16(lane_off + tA_lo + 16 * c, lo);
+        }
+        wait_st();
+        srow[t] = row_c;
+        fence_before_sync();
+        named_bar(bar_id, 128);     // A operand complete; everyone is done with qbuf[b^1] and with D of the last tile
+
+        // ---- MMA 1 + prefetch of the next tile's neighbour rows -----------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_gemm_3xtf32(tD, tA_hi, tA_lo, dW2hi, dW2lo, idesc, mbar);
+        }
+        __syncwarp();
+        int row_n, col_n;
+        float ea_n[DISTEGNN_MAX_EDGE_ATTR];
+        load_meta(tile + stride, row_n, col_n, ea_n);
+        prefetch_q(tile + stride, row_n, col_n, qbuf[b ^ 1], &qbar[b ^ 1]);
+
+        mbar_wait(mbar, 0);
+        __syncwarp();
+        fence_after_sync();
+
+        // ---- stage 2: m = SiLU(D + b2) -------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t d[16], hi[16], lo[16];
+            tmem_ld16(lane_off + tD + 16 * c, d);
+            wait_ld();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * c + 4 * j4);
+                float4 m;
+                m.x = silu(__uint_as_float(d[4 * j4 + 0]) + bb.x);
+                m.y = silu(__uint_as_float(d[4 * j4 + 1]) + bb.y);
+                m.z = silu(__uint_as_float(d[4 * j4 + 2]) + bb.z);
+                m.w = silu(__uint_as_float(d[4 * j4 + 3]) + bb.w);
+                if (need_m) *reinterpret_cast<float4*>(qb + t * QROW + 16 * c + 4 * j4) = m;
+                split_tf32(m.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
+                split_tf32(m.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
+                split_tf32(m.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
+                split_tf32(m.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
+            }
+            tmem_st16(lane_off + tA_hi + 16 * c, hi);
+            tmem_st16(lane_off + tA_lo + 16 * c, lo);
+        }
+        wait_st();
+        fence_before_sync();
+        named_bar(bar_id, 128);     // m tile visible in shared, A operand complete, D fully read
+
+        // ---- MMA 2 (φ head) overlapped with the segment sum of m ---------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_gemm_3xtf32(tD, tA_hi, tA_lo, dWchi, dWclo, idesc, mbar);
+        }
+        __syncwarp();
+        if (need_m) {
+            const int c = t & 63, eb = (t >> 6) * 64;
+            int cur = srow[eb];
+            float s = 0.f;
+#pragma unroll 8
+            for (int e = eb; e < eb + 64; ++e) {
+                const int r = srow[e];
+                if (r != cur) {
+                    if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s);
+                    s = 0.f;
+                    cur = r;
+                }
+                s += qb[e * QROW + c];
+            }
+            if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s);
+            fence_proxy_async_smem();   // generic accesses to qb ordered before its next TMA refill
+        }
+
+        mbar_wait(mbar, 1);
+        __syncwarp();
+        fence_after_sync();
+
+        // ---- stage 3: φ = w3·SiLU(D + bc); Δx·φ summed per destination row --------------------------
+        float phi = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t d[16];
+            tmem_ld16(lane_off + tD + 16 * c, d);
+            wait_ld();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bcs + 16 * c + 4 * j4);
+                const float4 ww = *reinterpret_cast<const float4*>(w3s + 16 * c + 4 * j4);
+                phi = fmaf(silu(__uint_as_float(d[4 * j4 + 0]) + bb.x), ww.x, phi);
+                phi = fmaf(silu(__uint_as_float(d[4 * j4 + 1]) + bb.y), ww.y, phi);
+                phi = fmaf(silu(__uint_as_float(d[4 * j4 + 2]) + bb.z), ww.z, phi);
+                phi = fmaf(silu(__uint_as_float(d[4 * j4 + 3]) + bb.w), ww.w, phi);
+            }
+        }
+        {
+            float sx = dx * phi, sy = dy * phi, sz = dz * phi;
+            // inclusive segmented scan over the warp (keys sorted): lane adds lanes below with the same row
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int rk = __shfl_up_sync(FULL, row_c, o);
+                const float ox = __shfl_up_sync(FULL, sx, o), oy = __shfl_up_sync(FULL, sy, o),
+                            oz = __shfl_up_sync(FULL, sz, o);
+                if (lane >= o && rk == row_c) { sx += ox; sy += oy; sz += oz; }
+            }
+            const int rnext = __shfl_down_sync(FULL, row_c, 1);
+            if (valid && (lane == 31 || rnext != row_c)) {
+                float* dst = a.agg_x + (size_t)row_c * 4;
+                atomicAdd(dst + 0, sx);
+                atomicAdd(dst + 1, sy);
+                atomicAdd(dst + 2, sz);
+            }
+        }
+        fence_before_sync();   // D reads ordered before the next tile's MMA (after the next named barrier)
+
+        row_c = row_n; col_c = col_n;
+#pragma unroll
+        for (int k = 0; k < DISTEGNN_MAX_EDGE_ATTR; ++k) ea_c[k] = ea_n[k];
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace degnn
+
+extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+                                       const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
+                                       const float* x4, const float* P, const float* Q,
+                                       const float* layer_params, float* agg_m, float* agg_x, void* stream) {
+    using namespace degnn;
+    if (int rc = check_dims(A, C, Na)) return rc;
+    if (n_edges == 0) return DISTEGNN_OK;
+    DEGNN_CHECK_ARG(n_nodes > 0 && n_edges > 0, "negative size");
+    DEGNN_CHECK_ARG(row && col && x4 && P && Q && layer_params && agg_x, "null pointer");
+    DEGNN_CHECK_ARG(A == 0 || edge_attr_sorted, "null edge_attr with edge_attr_nf > 0");
+    DEGNN_CHECK_ARG((flags & DISTEGNN_FLAG_LAST) || agg_m, "null agg_m");
+    Layout L = make_layout(A, C, Na);
+    EdgeTcArgs a;
+    a.N = n_nodes; a.E = n_edges; a.A = A; a.flags = flags;
+    a.row = row; a.col = col; a.ea = edge_attr_sorted; a.x4 = x4; a.P = P; a.Q = Q;
+    a.w1r = layer_params + L.off[DISTEGNN_P_E_W1R];
+    a.w1e = layer_params + L.off[DISTEGNN_P_E_W1E];
+    a.w2 = layer_params + L.off[DISTEGNN_P_E_W2];
+    a.b2 = layer_params + L.off[DISTEGNN_P_E_B2];
+    a.wc = layer_params + L.off[DISTEGNN_P_E_WC];
+    a.bc = layer_params + L.off[DISTEGNN_P_E_BC];
+    a.w3 = layer_params + L.off[DISTEGNN_P_E_W3];
+    a.agg_m = agg_m; a.agg_x = agg_x;
+    cudaFuncSetAttribute(edge_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    const int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
+    int64_t grid = (tiles + 1) / 2;
+    if (grid > sm_count()) grid = sm_count();
+    edge_layer_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    DEGNN_CHECK_LAUNCH();
+    return DISTEGNN_OK;
+}

@@ -160,6 +160,19 @@ DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A
                             const float *x4, const float *P, const float *Q,
                             const float *layer_params, float *agg_m, float *agg_x, void *stream);
 
+/* Same contract as distegnn_edge_layer_fwd, computed with fp32 FMA on the CUDA cores (no tensor cores).
+ * Kept as an independent implementation for cross-checks of the tcgen05 kernel at sizes the CPU oracle
+ * cannot reach; not used by FastEGNN.forward. */
+DISTEGNN_API int distegnn_edge_layer_fwd_simt(int64_t n_nodes, int64_t n_edges, int A, int C, int Na,
+                                              unsigned flags, const int32_t *row, const int32_t *col,
+                                              const float *edge_attr_sorted, const float *x4, const float *P,
+                                              const float *Q, const float *layer_params, float *agg_m,
+                                              float *agg_x, void *stream);
+
+/* tcgen05 building-block self-test: D[128,64] = A[128,64]·W[64,64]^T on the tensor cores (variant 0:
+ * 3xTF32 with A in TMEM, as the fused kernels use it; 2: A in shared memory; 4/6: single-pass TF32). */
+DISTEGNN_API int distegnn_selftest_umma(const float *A, const float *W, float *D, int variant, void *stream);
+
 /* ---- real↔virtual stage --------------------------------------------------------------------------
  * Virtual geometry + edge_mode_virtual + the virtual parts of coord_model_vel, coord_model_virtual,
  * node_model and node_model_virtual (FastEGNN.py:252-253, 154-163, 180, 191-193, 207, 220-223):

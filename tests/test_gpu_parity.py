@@ -60,6 +60,59 @@ def test_library_loaded_and_abi():
     assert lib.distegnn_abi_version() == 1
 
 
+def test_tcgen05_building_block():
+    """D = A·Wᵀ on the tensor cores with the 3xTF32 split must be fp32-accurate (and plain TF32 must not
+    be — that is why the split exists)."""
+    import ctypes
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 64, generator=g).to(dev())
+    W = (torch.randn(64, 64, generator=g) / 8).to(dev())
+    ref = A.double() @ W.double().t()
+    errs = {}
+    for variant in (0, 2, 4):
+        D = torch.zeros(128, 64, device=dev())
+        rc = lib.distegnn_selftest_umma(A.data_ptr(), W.data_ptr(), D.data_ptr(), variant,
+                                        torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        errs[variant] = max_abs(D, ref)
+    print("tcgen05 selftest errs", errs)
+    assert errs[0] <= 1e-5 and errs[2] <= 1e-5      # 3xTF32, A in TMEM / in shared memory
+    assert errs[4] > 1e-4                           # single-pass TF32 is not fp32-accurate
+
+
+def test_edge_kernel_tensor_core_vs_fma_twin():
+    """The tcgen05 edge kernel against its independent fp32-FMA implementation on a 300k-node graph
+    (both normalisation modes, with and without the Σm output)."""
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    w = synth.WORKLOADS["synth1m"]
+    inp = to_dev(synth.make_partitions(w, n_nodes=300_000, seed=7)[0])
+    sd = orc.init_state_dict(3, 2, 2, 64, 8, 1, seed=2, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=2, edge_attr_nf=2, virtual_channels=8, n_layers=1), sd)
+    lp = m._packed_params(dev())["layers"][0]
+    N, E = inp["node_loc"].shape[0], inp["edge_index"].shape[1]
+    rowptr, row, col, perm = be.build_csr(inp["edge_index"], N)
+    ea = be.gather_rows(inp["edge_attr"], perm)
+    g = torch.Generator().manual_seed(3)
+    P, Q = torch.randn(N, 64, generator=g).to(dev()), torch.randn(N, 64, generator=g).to(dev())
+    x4 = torch.zeros(N, 4, device=dev())
+    x4[:, :3] = inp["node_loc"]
+    for flags in (0, _lib.FLAG_NORMALIZE, _lib.FLAG_LAST):
+        outs = []
+        for fn in (be.edge_layer, be.edge_layer_simt):
+            agg_m, agg_x = torch.zeros(N, 64, device=dev()), torch.zeros(N, 4, device=dev())
+            fn((N, E, 2, 8, 2), flags, row, col, ea, x4, P, Q, lp, None if flags & _lib.FLAG_LAST else agg_m,
+               agg_x)
+            torch.cuda.synchronize()
+            outs.append((agg_m, agg_x))
+        em = max_abs(outs[0][0], outs[1][0]) / max(1e-9, float(outs[1][0].abs().max()))
+        ex = max_abs(outs[0][1], outs[1][1]) / max(1e-9, float(outs[1][1].abs().max()))
+        print(f"flags {flags}: rel err agg_m {em:.3e} agg_x {ex:.3e}")
+        assert em <= 1e-5 and ex <= 1e-5
+
+
 @pytest.mark.parametrize("name", SINGLE_CASES)
 def test_golden_fixtures(name):
     z, kw, sd = load_golden(name)
