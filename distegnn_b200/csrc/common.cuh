@@ -46,8 +46,12 @@ int sm_count();   // cached multiprocessor count of the current device
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float silu(float x) {
-    // x·σ(x) = x / (1 + e^{-x}); ex2.approx + rcp.approx, |rel err| ≲ 1e-6
-    return __fdividef(x, 1.0f + __expf(-x));
+    // x·σ(x) = x · rcp(1 + 2^{-x·log2 e}): FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL — no range fix-ups needed:
+    // x → −∞ gives 2^{+big} = inf, rcp(inf) = 0, x·0 = −0;  x → +∞ gives rcp(1) = 1.  |rel err| ≲ 5e-7.
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
 }
 __device__ __forceinline__ float4 silu4(float4 v) {
     return make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));

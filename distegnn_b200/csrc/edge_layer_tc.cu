@@ -3,8 +3,9 @@
 // cross-checks); replaces reference models/FastEGNN.py:237-246,144-150,169-177,206 and the scatter_add_ of
 // :322-337.
 //
-// One CTA per SM, 256 threads = 2 independent warpgroups (WG).  A WG owns one 128-edge tile at a time;
-// thread r of the WG owns edge r of the tile end to end (TMEM lane r):
+// One CTA per SM, 512 threads = 2 independent tile groups of 8 warps.  A group owns one 128-edge tile at a
+// time; edge r of the tile lives in TMEM lane r and is handled by TWO threads (warps q and q+4 of the group
+// share TMEM lane quarter q and split the 64 feature columns 32/32 — twice the warps for the same TMEM):
 //   stage 0  the 256-byte neighbour rows Q[col] of the NEXT tile are fetched by the TMA engine
 //            (cp.async.bulk global->shared, one copy per edge, completion on an mbarrier) while the
 //            current tile computes — the [E,64] gathers of the reference never exist;
@@ -43,13 +44,15 @@ struct EdgeTcArgs {
     float* agg_x;
 };
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;                           // 2 tile groups x 8 warps
+constexpr int GROUP_THREADS = 256;                        // warps (q, half): TMEM lane quarter q, column half
 constexpr int QROW = 68;                                  // floats per staged row (272 B: 16B-aligned, bank-shifted)
 constexpr int QBUF_FLOATS = TILE_M * QROW;                // 8704
 constexpr int TC_SMEM_BYTES = 4 * 16384                   // W2 hi/lo, Wc hi/lo (UMMA canonical layout)
-                              + 2 * 2 * QBUF_FLOATS * 4   // 2 WGs x 2 staging buffers
+                              + 2 * 2 * QBUF_FLOATS * 4   // 2 groups x 2 staging buffers
                               + (4 * H + DISTEGNN_MAX_EDGE_ATTR * H) * 4   // b2, bc, w3, w1r, w1e
-                              + 2 * 2 * TILE_M * 4        // srow per WG, double-buffered by tile parity
+                              + 2 * 2 * TILE_M * 4        // srow per group, double-buffered by tile parity
+                              + 2 * 2 * TILE_M * 4        // partial φ per group and column half
                               + 64;                       // mbarriers + tmem base
 
 __device__ __forceinline__ void stage_weight_umma(float* hi, float* lo, const float* __restrict__ wt_kmajor,
@@ -85,21 +88,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
     float* W2lo = W2hi + 4096;
     float* Wchi = W2lo + 4096;
     float* Wclo = Wchi + 4096;
-    float* qbufs = Wclo + 4096;                               // [2 WG][2][QBUF_FLOATS]
+    float* qbufs = Wclo + 4096;                               // [2 groups][2][QBUF_FLOATS]
     float* b2s = qbufs + 4 * QBUF_FLOATS;
     float* bcs = b2s + H;
     float* w3s = bcs + H;
     float* w1rs = w3s + H;
     float* w1es = w1rs + H;                                   // [A][64]
-    int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);   // [2 WG][2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(srow_all + 4 * TILE_M);         // [2 WG][3]
+    int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);   // [2 groups][2][128]
+    float* phi_all = reinterpret_cast<float*>(srow_all + 4 * TILE_M);             // [2 groups][2 halves][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(phi_all + 4 * TILE_M);          // [2 groups][3]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x;
-    const int wg = tid >> 7;               // warpgroup 0/1
-    const int t = tid & 127;               // row owned inside the tile
+    const int grp = tid >> 8;              // tile group 0/1 (each owns one 128-edge tile at a time)
+    const int u = tid & 255;               // thread index inside the group
     const int lane = tid & 31;
-    const int wq = (tid >> 5) & 3;         // warp index inside the WG == TMEM lane quarter
+    const int w8 = u >> 5;                 // warp inside the group
+    const int wq = w8 & 3;                 // TMEM lane quarter (== warp id % 4, a hardware rule)
+    const int half = w8 >> 2;              // which 32 of the 64 feature columns this warp handles
+    const int t = 32 * wq + lane;          // edge (row) of the tile owned by this thread
+    const int cb = 32 * half;              // first feature column of this thread
     const int A = a.A;
     const bool normalize = a.flags & DISTEGNN_FLAG_NORMALIZE;
     const bool need_m = !(a.flags & DISTEGNN_FLAG_LAST);
@@ -126,21 +134,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
     fence_after_sync();
 
     const uint32_t tbase = *tmem_base_s;
-    const uint32_t col0 = tbase + (uint32_t)wg * 256u;             // this WG's TMEM columns
+    const uint32_t col0 = tbase + (uint32_t)grp * 256u;            // this group's TMEM columns
     const uint32_t tA_hi = col0, tA_lo = col0 + 64, tD = col0 + 128;
     const uint32_t lane_off = ((uint32_t)(32 * wq)) << 16;          // this warp's TMEM lane quarter
     const uint32_t idesc = make_idesc_tf32(128, 64);
     const uint64_t dW2hi = make_b_desc(smem_u32(W2hi), B_LBO, B_SBO), dW2lo = make_b_desc(smem_u32(W2lo), B_LBO, B_SBO);
     const uint64_t dWchi = make_b_desc(smem_u32(Wchi), B_LBO, B_SBO), dWclo = make_b_desc(smem_u32(Wclo), B_LBO, B_SBO);
-    float* qbuf[2] = {qbufs + (wg * 2 + 0) * QBUF_FLOATS, qbufs + (wg * 2 + 1) * QBUF_FLOATS};
-    int* srow2 = srow_all + wg * 2 * TILE_M;
-    uint64_t* qbar = bars + wg * 3;        // [2]
-    uint64_t* mbar = bars + wg * 3 + 2;
-    const uint32_t bar_id = 1 + wg;
+    float* qbuf0 = qbufs + (grp * 2 + 0) * QBUF_FLOATS;
+    int* srow2 = srow_all + grp * 2 * TILE_M;
+    float* phis = phi_all + grp * 2 * TILE_M;
+    uint64_t* qbar = bars + grp * 3;       // [2]
+    uint64_t* mbar = bars + grp * 3 + 2;
+    const uint32_t bar_id = 1 + grp;
 
     const int64_t num_tiles = (a.E + TILE_M - 1) / TILE_M;
     const int64_t stride = (int64_t)gridDim.x * 2;
-    int64_t tile = (int64_t)blockIdx.x * 2 + wg;
+    int64_t tile = (int64_t)blockIdx.x * 2 + grp;
 
     // metadata of the tile about to be processed (registers) and of the prefetched one
     int row_c = -1, col_c = 0;
@@ -157,8 +166,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
                 if (k < A) ea[k] = __ldg(a.ea + e * A + k);
         }
     };
+    // neighbour rows Q[col] of tile `tl` -> staging buffer, one TMA bulk copy per edge (column-half-0 warps)
     auto prefetch_q = [&](int64_t tl, int r, int c, float* dst, uint64_t* bar) {
-        if (tl < num_tiles) {
+        if (tl < num_tiles && half == 0) {
             if (t == 0) {
                 const int64_t nvalid = min((int64_t)TILE_M, a.E - tl * TILE_M);
                 mbar_expect_tx(bar, (uint32_t)nvalid * (H * 4));
@@ -169,16 +179,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
 
     if (tile < num_tiles) {
         load_meta(tile, row_c, col_c, ea_c);
-        prefetch_q(tile, row_c, col_c, qbuf[0], &qbar[0]);
+        prefetch_q(tile, row_c, col_c, qbuf0, &qbar[0]);
     }
 
     for (int it = 0; tile < num_tiles; ++it, tile += stride) {
         const int b = it & 1;
-        float* qb = qbuf[b];
-        int* srow = srow2 + b * TILE_M;   // read by this tile's segment sum until the next-but-one tile
+        float* qb = qbuf0 + b * QBUF_FLOATS;
+        int* srow = srow2 + b * TILE_M;    // read by this tile's segment sum until the next-but-one tile
         const bool valid = row_c >= 0;
 
-        // ---- stage 1 ---------------------------------------------------------------------------
+        // ---- stage 1: a1 = SiLU(P_i + Q_j + w_r·r + W_e·a) for this thread's 32 columns ---------------
         float dx = 0.f, dy = 0.f, dz = 0.f, radial = 0.f;
         if (valid) {
             const float4 xi = ldg4(a.x4 + (size_t)row_c * 4), xj = ldg4(a.x4 + (size_t)col_c * 4);
@@ -192,20 +202,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
         mbar_wait(&qbar[b], (uint32_t)((it >> 1) & 1));
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+            const int cc = cb + 16 * c;
             uint32_t hi[16], lo[16];
             if (valid) {
-                const float* prow = a.P + (size_t)row_c * H + 16 * c;
-                const float* qrow = qb + t * QROW + 16 * c;
+                const float* prow = a.P + (size_t)row_c * H + cc;
+                const float* qrow = qb + t * QROW + cc;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 p = ldg4(prow + 4 * j4);
                     const float4 q = *reinterpret_cast<const float4*>(qrow + 4 * j4);
-                    float4 pre = fma4(radial, *reinterpret_cast<const float4*>(w1rs + 16 * c + 4 * j4), add4(p, q));
+                    float4 pre = fma4(radial, *reinterpret_cast<const float4*>(w1rs + cc + 4 * j4), add4(p, q));
 #pragma unroll
                     for (int k = 0; k < DISTEGNN_MAX_EDGE_ATTR; ++k)
-                        if (k < A)
-                            pre = fma4(ea_c[k], *reinterpret_cast<const float4*>(w1es + k * H + 16 * c + 4 * j4), pre);
+                        if (k < A) pre = fma4(ea_c[k], *reinterpret_cast<const float4*>(w1es + k * H + cc + 4 * j4), pre);
                     pre = silu4(pre);
                     split_tf32(pre.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
                     split_tf32(pre.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
@@ -217,16 +227,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
                 for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0u;
             }
             __syncwarp();
-            tmem_st16(lane_off + tA_hi + 16 * c, hi);
-            tmem_st16(lane_off + tA_lo + 16 * c, lo);
+            tmem_st16(lane_off + tA_hi + cc, hi);
+            tmem_st16(lane_off + tA_lo + cc, lo);
         }
         wait_st();
-        srow[t] = row_c;
+        if (half == 0) srow[t] = row_c;
         fence_before_sync();
-        named_bar(bar_id, 128);     // A operand complete; everyone is done with qbuf[b^1] and with D of the last tile
+        named_bar(bar_id, GROUP_THREADS);   // A complete; group is done with the other staging buffer and with D
 
         // ---- MMA 1 + prefetch of the next tile's neighbour rows -----------------------------------
-        if (t == 0) {
+        if (u == 0) {
             fence_after_sync();
             issue_gemm_3xtf32(tD, tA_hi, tA_lo, dW2hi, dW2lo, idesc, mbar);
         }
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
         int row_n, col_n;
         float ea_n[DISTEGNN_MAX_EDGE_ATTR];
         load_meta(tile + stride, row_n, col_n, ea_n);
-        prefetch_q(tile + stride, row_n, col_n, qbuf[b ^ 1], &qbar[b ^ 1]);
+        prefetch_q(tile + stride, row_n, col_n, qbuf0 + (b ^ 1) * QBUF_FLOATS, &qbar[b ^ 1]);
 
         mbar_wait(mbar, 0);
         __syncwarp();
@@ -242,43 +252,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
 
         // ---- stage 2: m = SiLU(D + b2) -------------------------------------------------------------
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+            const int cc = cb + 16 * c;
             uint32_t d[16], hi[16], lo[16];
-            tmem_ld16(lane_off + tD + 16 * c, d);
+            tmem_ld16(lane_off + tD + cc, d);
             wait_ld();
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * c + 4 * j4);
+                const float4 bb = *reinterpret_cast<const float4*>(b2s + cc + 4 * j4);
                 float4 m;
                 m.x = silu(__uint_as_float(d[4 * j4 + 0]) + bb.x);
                 m.y = silu(__uint_as_float(d[4 * j4 + 1]) + bb.y);
                 m.z = silu(__uint_as_float(d[4 * j4 + 2]) + bb.z);
                 m.w = silu(__uint_as_float(d[4 * j4 + 3]) + bb.w);
-                if (need_m) *reinterpret_cast<float4*>(qb + t * QROW + 16 * c + 4 * j4) = m;
+                if (need_m) *reinterpret_cast<float4*>(qb + t * QROW + cc + 4 * j4) = m;
                 split_tf32(m.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
                 split_tf32(m.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
                 split_tf32(m.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
                 split_tf32(m.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
             }
-            tmem_st16(lane_off + tA_hi + 16 * c, hi);
-            tmem_st16(lane_off + tA_lo + 16 * c, lo);
+            tmem_st16(lane_off + tA_hi + cc, hi);
+            tmem_st16(lane_off + tA_lo + cc, lo);
         }
         wait_st();
         fence_before_sync();
-        named_bar(bar_id, 128);     // m tile visible in shared, A operand complete, D fully read
+        named_bar(bar_id, GROUP_THREADS);   // m tile visible in shared, A operand complete, D fully read
 
         // ---- MMA 2 (φ head) overlapped with the segment sum of m ---------------------------------
-        if (t == 0) {
+        if (u == 0) {
             fence_after_sync();
             issue_gemm_3xtf32(tD, tA_hi, tA_lo, dWchi, dWclo, idesc, mbar);
         }
         __syncwarp();
         if (need_m) {
-            const int c = t & 63, eb = (t >> 6) * 64;
+            const int c = u & 63, eb = (u >> 6) * 32;
             int cur = srow[eb];
             float s = 0.f;
 #pragma unroll 8
-            for (int e = eb; e < eb + 64; ++e) {
+            for (int e = eb; e < eb + 32; ++e) {
                 const int r = srow[e];
                 if (r != cur) {
                     if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s);
@@ -298,21 +309,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
         // ---- stage 3: φ = w3·SiLU(D + bc); Δx·φ summed per destination row --------------------------
         float phi = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+            const int cc = cb + 16 * c;
             uint32_t d[16];
-            tmem_ld16(lane_off + tD + 16 * c, d);
+            tmem_ld16(lane_off + tD + cc, d);
             wait_ld();
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 bb = *reinterpret_cast<const float4*>(bcs + 16 * c + 4 * j4);
-                const float4 ww = *reinterpret_cast<const float4*>(w3s + 16 * c + 4 * j4);
+                const float4 bb = *reinterpret_cast<const float4*>(bcs + cc + 4 * j4);
+                const float4 ww = *reinterpret_cast<const float4*>(w3s + cc + 4 * j4);
                 phi = fmaf(silu(__uint_as_float(d[4 * j4 + 0]) + bb.x), ww.x, phi);
                 phi = fmaf(silu(__uint_as_float(d[4 * j4 + 1]) + bb.y), ww.y, phi);
                 phi = fmaf(silu(__uint_as_float(d[4 * j4 + 2]) + bb.z), ww.z, phi);
                 phi = fmaf(silu(__uint_as_float(d[4 * j4 + 3]) + bb.w), ww.w, phi);
             }
         }
-        {
+        fence_before_sync();   // D reads ordered before the next tile's MMA (after the next named barrier)
+        if (half == 1) phis[t] = phi;
+        named_bar(bar_id, GROUP_THREADS);
+        if (half == 0) {
+            phi += phis[t];
             float sx = dx * phi, sy = dy * phi, sz = dz * phi;
             // inclusive segmented scan over the warp (keys sorted): lane adds lanes below with the same row
 #pragma unroll
@@ -330,7 +346,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
                 atomicAdd(dst + 2, sz);
             }
         }
-        fence_before_sync();   // D reads ordered before the next tile's MMA (after the next named barrier)
 
         row_c = row_n; col_c = col_n;
 #pragma unroll
