@@ -1,0 +1,50 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/distegnn_b200.h
+declares; the Python binding table covers them all; the host-only entry points work."""
+import ctypes
+import os
+import re
+
+from distegnn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "distegnn_b200.h")).read()
+    return sorted(set(re.findall(r"DISTEGNN_API\s+[\w\s\*]+?\b(distegnn_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ["distegnn_build_csr", "distegnn_edge_layer_fwd", "distegnn_virtual_layer_fwd",
+                 "distegnn_node_layer_fwd", "distegnn_virtual_update_fwd", "distegnn_embed_fwd",
+                 "distegnn_param_layout", "distegnn_last_error", "distegnn_abi_version"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_python_binding_table_matches_header():
+    bound = set(_lib.SIGNATURES) | {"distegnn_last_error"}
+    assert bound == set(declared_symbols())
+
+
+def test_host_only_entry_points():
+    lib = _lib.load()
+    assert lib.distegnn_abi_version() == 1
+    offs, total = _lib.param_layout(2, 8, 2)
+    assert total > 0 and offs["E_W1A"] == 0
+    # error convention: negative code + message, ValueError on the Python side for bad arguments
+    o = (ctypes.c_int64 * len(_lib.P_FIELDS))()
+    t = ctypes.c_int64(0)
+    rc = lib.distegnn_param_layout(2, 99, 0, o, ctypes.byref(t))
+    assert rc == -1 and b"virtual_channels" in lib.distegnn_last_error()
+    try:
+        _lib.param_layout(2, 99, 0)
+        assert False
+    except ValueError:
+        pass
