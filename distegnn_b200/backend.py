@@ -88,6 +88,13 @@ class CudaBackend:
                                                   ptr(vsum), self._s(x4)), "virtual_layer_fwd")
         self.launches += 1 if N else 0
 
+    def virtual_layer_simt(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
+        """fp32-FMA twin of virtual_layer (cross-check only)."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_layer_fwd_simt(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
+                                                       ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
+                                                       ptr(vsum), self._s(x4)), "virtual_layer_fwd_simt")
+
     def node_layer(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
                    lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum) -> None:
         N, B, A, Cn, Na = dims

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) virtual_layer_kernel(const VirtAr
 
 }  // namespace degnn
 
-extern "C" int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na,
+extern "C" int distegnn_virtual_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na,
                                           unsigned flags, const int32_t* batch32, const float* x4,
                                           const float* Hn, const float* Xv, const float* G,
                                           const float* layer_params, float* agg_v, float* trans_v,

@@ -113,6 +113,39 @@ def test_edge_kernel_tensor_core_vs_fma_twin():
         assert em <= 1e-5 and ex <= 1e-5
 
 
+@pytest.mark.parametrize("C,B", [(8, 1), (5, 1), (3, 7)])
+def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
+    """tcgen05 virtual-stage kernel against its fp32-FMA twin (single graph and a batch whose tiles
+    straddle graph boundaries; C = 8 / 5 / 3 exercise full and ragged row tiles)."""
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    N = 100_003
+    g = torch.Generator().manual_seed(C)
+    sd = orc.init_state_dict(3, 0, 2, 64, C, 1, seed=5, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=0, edge_attr_nf=2, virtual_channels=C, n_layers=1), sd)
+    lp = m._packed_params(dev())["layers"][0]
+    d = dev()
+    batch = torch.sort(torch.randint(0, B, (N,), generator=g))[0].to(torch.int32).to(d)
+    x4 = torch.zeros(N, 4, device=d)
+    x4[:, :3] = torch.randn(N, 3, generator=g).to(d)
+    Hn = torch.randn(N, 64, generator=g).to(d)
+    Xv = torch.randn(B, 3, C, generator=g).to(d)
+    G = torch.randn(B, C, 64, generator=g).to(d)
+    K = 4 + 3 * C + 64 * C
+    for flags in (0, _lib.FLAG_LAST):
+        outs = []
+        for fn in (be.virtual_layer, be.virtual_layer_simt):
+            agg_v, trans_v = torch.zeros(N, 64, device=d), torch.zeros(N, 4, device=d)
+            vsum = torch.zeros(B, K, device=d)
+            fn((N, B, 2, C, 0), flags, batch, x4, Hn, Xv, G, lp, None if flags else agg_v, trans_v, vsum)
+            torch.cuda.synchronize()
+            outs.append((agg_v, trans_v[:, :3], vsum))
+        for name, x, y in zip(("agg_v", "trans_v", "vsum"), outs[0], outs[1]):
+            err = max_abs(x, y) / max(1e-9, float(y.abs().max()))
+            print(f"C={C} B={B} flags={flags} {name}: rel err {err:.3e}")
+            assert err <= 2e-5, (name, err)
+
+
 @pytest.mark.parametrize("name", SINGLE_CASES)
 def test_golden_fixtures(name):
     z, kw, sd = load_golden(name)
