@@ -1,0 +1,82 @@
+"""Multi-GPU parity: run under torchrun with N ranks (one per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        scripts/dist_parity.py [--workload fluid113k] [--nodes 113140] [--split-mode random|kmeans]
+
+Every rank builds the same seeded graph, takes its partition (distribute_graphs.py semantics restated in
+distegnn_b200/synth.py), runs FastEGNN(world_size=N) through the CUDA path with the packed NCCL all-reduce, and
+rank 0 compares all ranks' outputs with the oracle evaluated on the P partitions in one process
+(== the reference's world_size=N branch, see tests/test_oracle_golden.py).
+"""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from distegnn_b200 import FastEGNN, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="fluid113k")
+    ap.add_argument("--nodes", type=int, default=None)
+    ap.add_argument("--split-mode", default="random")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    w = synth.WORKLOADS[args.workload]
+    parts = synth.make_partitions(w, world_size=world, split_mode=args.split_mode, seed=11, n_nodes=args.nodes)
+    from oracle import fastegnn_oracle as orc
+    sd = orc.init_state_dict(w.node_feat_nf, w.node_attr_nf, w.edge_attr_nf, 64, w.virtual_channels, 4, seed=3,
+                             coord_gain=0.05)
+    m = FastEGNN(node_feat_nf=w.node_feat_nf, node_attr_nf=w.node_attr_nf, edge_attr_nf=w.edge_attr_nf,
+                 hidden_nf=64, virtual_channels=w.virtual_channels, world_size=world, n_layers=4,
+                 normalize=w.normalize)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    inp = {k: (v.to(dev) if v is not None else None) for k, v in parts[rank].items()}
+    with torch.no_grad():
+        out, X = m(**inp)
+    torch.cuda.synchronize()
+    sizes = [p["node_loc"].shape[0] for p in parts]
+    gathered = [torch.empty(n, 3, device=dev) for n in sizes]
+    # all_gather with uneven sizes: pad to max
+    mx = max(sizes)
+    pad = torch.zeros(mx, 3, device=dev)
+    pad[:out.shape[0]] = out
+    bufs = [torch.empty(mx, 3, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    Xs = [torch.empty_like(X) for _ in range(world)]
+    dist.all_gather(Xs, X)
+    ok = True
+    if rank == 0:
+        sd64 = {k: v.double() for k, v in sd.items()}
+        p64 = [{k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in p.items()}
+               for p in parts]
+        refs, refX = orc.forward_partitions(sd64, [{k: v for k, v in p.items() if k != "loc_mean"} for p in p64],
+                                            p64[0]["loc_mean"], normalize=w.normalize)
+        for r in range(world):
+            o = bufs[r][:sizes[r]].cpu().double()
+            err = float((o - refs[r]).abs().max())
+            disp = float((refs[r] - p64[r]["node_loc"]).abs().max())
+            ex = float((Xs[r].cpu().double() - refX).abs().max())
+            same = bool((Xs[r] == Xs[0]).all())
+            print(f"rank {r}: N={sizes[r]} E={parts[r]['edge_index'].shape[1]} max|out-ref64|={err:.3e} "
+                  f"rel-disp={err / disp:.3e} virtual={ex:.3e} virtual-bit-identical-to-rank0={same}", flush=True)
+            ok &= err <= 1e-5 * max(1.0, float(refs[r].abs().max())) and err / disp <= 1e-4 and ex <= 1e-5 and same
+        print("DIST_PARITY", "PASS" if ok else "FAIL", f"world={world} split={args.split_mode} {args.workload}",
+              flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
