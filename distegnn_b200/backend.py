@@ -88,6 +88,13 @@ class CudaBackend:
                                                   ptr(vsum), self._s(x4)), "virtual_layer_fwd")
         self.launches += 1 if N else 0
 
+    def edge_layer_tf32(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
+        """3xTF32 tensor-core twin of edge_layer (cross-check / A-B timing only)."""
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_fwd_tf32(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
+                                                    ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
+                                                    ptr(agg_x), self._s(x4)), "edge_layer_fwd_tf32")
+
     def virtual_layer_simt(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
         """fp32-FMA twin of virtual_layer (cross-check only)."""
         N, B, A, Cn, Na = dims

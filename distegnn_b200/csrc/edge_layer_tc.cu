@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) edge_layer_tc_kernel(const Edge
 
 }  // namespace degnn
 
-extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+extern "C" int distegnn_edge_layer_fwd_tf32(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q,
                                        const float* layer_params, float* agg_m, float* agg_x, void* stream) {

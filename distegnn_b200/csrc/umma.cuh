@@ -42,6 +42,37 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 variant: formats 0 = f16, 1 = bf16 (A at [7,10), B at [10,13)), fp32 accumulate, K = 16 per MMA
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 2-term 16-bit split of an fp32 value: x ≈ bf16(x) [truncated: top 16 bits] + fp16(x − bf16(x))
+// (8 + 11 significant bits, fp32 exponent range for the leading term)
+__device__ __forceinline__ void split_bf16_f16(float x, uint32_t& hi_bf16_bits, float& rem) {
+    hi_bf16_bits = __float_as_uint(x) & 0xFFFF0000u;
+    rem = x - __uint_as_float(hi_bf16_bits);
+}
+__device__ __forceinline__ uint32_t pack_bf16_trunc(uint32_t even_bits, uint32_t odd_bits) {
+    return (even_bits >> 16) | (odd_bits & 0xFFFF0000u);      // element k even in the low half
+}
+__device__ __forceinline__ uint32_t pack_f16(float even, float odd) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));   // first source -> upper half
+    return r;
+}
+
 // ---- TMEM allocation (one warp, whole warp executes) -----------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

@@ -3,6 +3,8 @@
 // K-major shared-memory descriptor.  Exposed through the C ABI so tests/test_gpu_parity.py can pin the
 // descriptor encodings on real hardware.
 #include "common.cuh"
+#include <cuda_fp16.h>
+
 #include "umma.cuh"
 
 namespace degnn {
@@ -119,6 +121,110 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
+// 16-bit split self-test: A = A1(bf16) + A2(fp16), W = W1(bf16) + W2(fp16); D = A2W2 + A2W1 + A1W2 + A1W1 in
+// kind::f16 (variant 8: mixed formats as described; variant 9: everything fp16 with 3 products).
+__global__ void __launch_bounds__(128, 1) umma_selftest16_kernel(const float* __restrict__ A,
+                                                                 const float* __restrict__ W,
+                                                                 float* __restrict__ D, int variant) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint16_t* B1 = reinterpret_cast<uint16_t*>(smem_raw);        // 8 KB: 64 x 64 x 2 B
+    uint16_t* B2 = B1 + 4096;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool all_f16 = (variant == 9);
+    // B element (n,k): (k/8)*1024 B + (n/8)*128 B + (n%8)*16 B + (k%8)*2 B
+    for (int i = tid; i < 64 * 64; i += 128) {
+        const int n = i >> 6, k = i & 63;
+        const float w = W[i];
+        const uint32_t o = (k >> 3) * 512 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+        if (all_f16) {
+            const __half h1 = __float2half_rn(w);
+            const __half h2 = __float2half_rn(w - __half2float(h1));
+            B1[o] = __half_as_ushort(h1);
+            B2[o] = __half_as_ushort(h2);
+        } else {
+            const uint32_t hb = __float_as_uint(w) & 0xFFFF0000u;
+            B1[o] = (uint16_t)(hb >> 16);
+            B2[o] = __half_as_ushort(__float2half_rn(w - __uint_as_float(hb)));
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
+    const uint32_t colA1 = 0, colA2 = 32, colD = 64;
+    const float* arow = A + (size_t)tid * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {        // 32 elements -> 16 packed columns per chunk
+        uint32_t p1[16], p2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float x0 = arow[32 * c + 2 * j], x1 = arow[32 * c + 2 * j + 1];
+            if (all_f16) {
+                const __half a0 = __float2half_rn(x0), a1 = __float2half_rn(x1);
+                p1[j] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
+                p2[j] = pack_f16(x0 - __half2float(a0), x1 - __half2float(a1));
+            } else {
+                uint32_t h0, h1;
+                float r0, r1;
+                split_bf16_f16(x0, h0, r0);
+                split_bf16_f16(x1, h1, r1);
+                p1[j] = pack_bf16_trunc(h0, h1);
+                p2[j] = pack_f16(r0, r1);
+            }
+        }
+        tmem_st16(lane_addr + colA1 + 16 * c, p1);
+        tmem_st16(lane_addr + colA2 + 16 * c, p2);
+    }
+    wait_st();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        fence_after_sync();
+        const int f1 = all_f16 ? 0 : 1;   // format of the leading terms: bf16 (1) or f16 (0)
+        const uint64_t d1 = make_b_desc(smem_u32(B1), 1024, 128), d2 = make_b_desc(smem_u32(B2), 1024, 128);
+        uint32_t acc = 0;
+        auto gemm = [&](uint32_t acol, uint64_t bd, int af, int bf) {
+            const uint32_t idesc = make_idesc_f16(128, 64, af, bf);
+            for (int ks = 0; ks < 4; ++ks) {      // K = 16 per MMA: 8 packed A columns, 2 K-chunks of B
+                mma_f16_ts(tbase + colD, tbase + acol + 8 * ks, bd + (uint64_t)ks * ((2 * 1024) >> 4), idesc, acc);
+                acc = 1;
+            }
+        };
+        if (!all_f16) gemm(colA2, d2, 0, 0);      // A2·W2 (f16 x f16)
+        gemm(colA2, d1, 0, f1);                   // A2·W1
+        gemm(colA1, d2, f1, 0);                   // A1·W2
+        gemm(colA1, d1, f1, f1);                  // A1·W1
+        mma_commit(&mbar);
+    }
+    __syncwarp();
+    mbar_wait(&mbar, 0);
+    __syncwarp();
+    fence_after_sync();
+    float* drow = D + (size_t)tid * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + colD + 16 * c, r);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) drow[16 * c + j] = __uint_as_float(r[j]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 128);
+}
+
 }  // namespace degnn
 
 extern "C" int distegnn_selftest_umma(const float* A, const float* W,
@@ -126,6 +232,11 @@ extern "C" int distegnn_selftest_umma(const float* A, const float* W,
                                                                               void* stream) {
     using namespace degnn;
     DEGNN_CHECK_ARG(A && W && D, "null pointer");
+    if (variant >= 8) {
+        umma_selftest16_kernel<<<1, 128, 2 * 8192, (cudaStream_t)stream>>>(A, W, D, variant);
+        DEGNN_CHECK_LAUNCH();
+        return DISTEGNN_OK;
+    }
     const int smem = 2 * 16384 + 2 * 32768;
     cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, variant);

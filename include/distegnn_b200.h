@@ -169,6 +169,14 @@ DISTEGNN_API int distegnn_edge_layer_fwd_simt(int64_t n_nodes, int64_t n_edges, 
                                               const float *Q, const float *layer_params, float *agg_m,
                                               float *agg_x, void *stream);
 
+/* Same contract, tensor-core implementation with the 3xTF32 split (earlier production kernel; kept for A/B
+ * measurements and as a third independent implementation in the cross-checks). */
+DISTEGNN_API int distegnn_edge_layer_fwd_tf32(int64_t n_nodes, int64_t n_edges, int A, int C, int Na,
+                                              unsigned flags, const int32_t *row, const int32_t *col,
+                                              const float *edge_attr_sorted, const float *x4, const float *P,
+                                              const float *Q, const float *layer_params, float *agg_m,
+                                              float *agg_x, void *stream);
+
 /* tcgen05 building-block self-test: D[128,64] = A[128,64]·W[64,64]^T on the tensor cores (variant 0:
  * 3xTF32 with A in TMEM, as the fused kernels use it; 2: A in shared memory; 4/6: single-pass TF32). */
 DISTEGNN_API int distegnn_selftest_umma(const float *A, const float *W, float *D, int variant, void *stream);
