@@ -40,6 +40,7 @@ SIGNATURES = {
     "distegnn_virtual_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_virtual_layer_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_node_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 20,
+    "distegnn_node_layer_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 20,
     "distegnn_virtual_update_fwd": [_i32, _i32, _i32, _i32, _u32] + [_vp] * 7,
 }
 

@@ -112,6 +112,16 @@ class CudaBackend:
                                                ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd")
         self.launches += 1 if N else 0
 
+    def node_layer_simt(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
+                        lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum) -> None:
+        """fp32-FMA twin of node_layer (cross-check only)."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_node_layer_fwd_simt(N, B, A, Cn, Na, flags, ptr(rowptr), ptr(batch32), ptr(h),
+                                                    ptr(x4), ptr(vel), ptr(attr), ptr(agg_m), ptr(agg_x),
+                                                    ptr(agg_v), ptr(trans_v), ptr(lp), ptr(lp_next),
+                                                    ptr(h_out), ptr(x4_out), ptr(P), ptr(Q), ptr(Hn),
+                                                    ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd_simt")
+
     def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G) -> None:
         B, A, Cn, Na = dims
         check(self.lib.distegnn_virtual_update_fwd(B, A, Cn, Na, flags, ptr(vsum), ptr(Xv), ptr(Hv),

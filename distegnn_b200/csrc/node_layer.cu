@@ -417,7 +417,7 @@ extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, i
     return DISTEGNN_OK;
 }
 
-extern "C" int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na,
+extern "C" int distegnn_node_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na,
                                        unsigned flags, const int32_t* rowptr, const int32_t* batch32,
                                        const float* h, const float* x4, const float* node_vel,
                                        const float* node_attr, const float* agg_m, const float* agg_x,

@@ -1,0 +1,127 @@
+// fp16 2-term split helpers shared by the tensor-core kernels (kind::f16 path).
+//   x = hi + lo,  hi = fp16(x),  lo = fp16(x − hi)          (22 significant bits)
+//   A·Wᵀ ≈ A_lo·W_hiᵀ + A_hi·W_loᵀ + A_hi·W_hiᵀ             (fp32 accumulation in TMEM)
+// A rows live in TMEM (lane = row, two fp16 per 32-bit column, even k in the low half); W lives in shared memory
+// in the canonical no-swizzle K-major layout for 16-bit types: core matrix = 8 rows x 8 halfs (128 B),
+// element (n,k) at (k/8)*LBO + (n/8)*128 B + (n%8)*16 B + (k%8)*2 B with LBO = (N/8)*128 B.
+// fp16 range: a row whose |max| exceeds 3e4 is re-encoded with a power-of-two scale s (cold path) and the
+// caller multiplies the accumulator row by 1/s — results stay range-safe like fp32.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace degnn {
+namespace tc16 {
+
+constexpr float RANGE = 3.0e4f;
+
+// stage W[n][k] (given k-major: wt[k*64+n]) as rows n_off..n_off+63 of an N_total-row B operand, fp16 hi/lo
+__device__ __forceinline__ void stage_weight(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int n_off,
+                                             int n_total, int tid, int nthreads) {
+    const uint32_t lbo_h = (uint32_t)(n_total / 8) * 64u;     // halfs per K chunk of 8
+    for (int i = tid; i < H * H; i += nthreads) {
+        const int k = i >> 6, n = (i & 63) + n_off;
+        const float w = __ldg(wt_kmajor + i);
+        const __half h = __float2half_rn(w);
+        const uint32_t o = (uint32_t)(k >> 3) * lbo_h + (uint32_t)(n >> 3) * 64u + (uint32_t)(n & 7) * 8u + (k & 7);
+        hi[o] = h;
+        lo[o] = __float2half_rn(w - __half2float(h));
+    }
+}
+__host__ __device__ constexpr uint32_t lbo_bytes(int n_total) { return (uint32_t)(n_total / 8) * 128u; }
+
+// 12 MMAs (K = 64 = 4 x 16): D (+)= A_lo·B_hiᵀ + A_hi·B_loᵀ + A_hi·B_hiᵀ.  `accumulate` = keep the old D.
+template <uint32_t LBO>
+__device__ __forceinline__ void issue_f16x3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                            uint32_t idesc, bool accumulate) {
+    constexpr uint64_t KSTEP = (2 * LBO) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        umma::mma_f16_ts(d, a_lo + 8 * ks, b_hi + ks * KSTEP, idesc, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) umma::mma_f16_ts(d, a_hi + 8 * ks, b_lo + ks * KSTEP, idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) umma::mma_f16_ts(d, a_hi + 8 * ks, b_hi + ks * KSTEP, idesc, 1u);
+}
+
+// 16 fp32 values (·s) -> 8 packed hi words + 8 packed lo words; `mx` tracks max |hi|
+template <bool SCALED>
+__device__ __forceinline__ void split16(const float (&v)[16], float s, uint32_t (&hi)[8], uint32_t (&lo)[8],
+                                        __half2& mx) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = SCALED ? v[2 * j] * s : v[2 * j], x1 = SCALED ? v[2 * j + 1] * s : v[2 * j + 1];
+        const __half2 h = __floats2half2_rn(x0, x1);            // x0 -> low half (even k)
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        mx = __hmax2(mx, __habs2(h));
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+__device__ __forceinline__ bool row_overflow(__half2 mx) {
+    return fmaxf(__low2float(mx), __high2float(mx)) > RANGE;
+}
+// power-of-two scale that brings |rowmax| below 2^15, and its inverse
+__device__ __forceinline__ void range_scale(float rowmax, float& s, float& inv_s) {
+    const uint32_t eb = (__float_as_uint(rowmax) >> 23) & 0xffu;
+    const uint32_t sb = eb > 141u ? 268u - eb : 127u;
+    s = __uint_as_float((sb < 1u ? 1u : sb) << 23);
+    inv_s = 1.0f / s;
+}
+
+// Encode one 64-wide fp32 row, produced 16 values at a time by f(chunk, v, first_pass), into the A operand
+// (TMEM columns ta_hi.. / ta_lo.., both including the warp's lane offset) with row scale `s_in` (a power of two
+// the row already carries, 1 normally).  Returns the scale actually used (<= s_in): smaller only if the row
+// would leave the fp16 range.  The caller issues tcgen05.wait::st afterwards and multiplies the accumulator row
+// by 1/scale in its epilogue.
+template <class F>
+__device__ __forceinline__ float encode_row_s(F&& f, uint32_t ta_hi, uint32_t ta_lo, float s_in) {
+    __half2 mx = __floats2half2_rn(0.f, 0.f);
+    const bool pre_scaled = __any_sync(FULL, s_in != 1.0f);
+    if (!pre_scaled) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[16];
+            uint32_t hi[8], lo[8];
+            f(c, v, true);
+            split16<false>(v, 1.0f, hi, lo, mx);
+            umma::tmem_st8(ta_hi + 8 * c, hi);
+            umma::tmem_st8(ta_lo + 8 * c, lo);
+        }
+        if (!__any_sync(FULL, row_overflow(mx))) return 1.0f;
+    }
+    // cold: some row of this warp carries a scale already or leaves the fp16 range
+    float fm = 0.f, sc, inv_unused;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+        f(c, v, pre_scaled && true);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) fm = fmaxf(fm, fabsf(v[j]));
+    }
+    range_scale(fm, sc, inv_unused);
+    sc = fminf(sc, s_in);
+    umma::wait_st();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+        uint32_t hi[8], lo[8];
+        f(c, v, false);
+        split16<true>(v, sc, hi, lo, mx);
+        umma::tmem_st8(ta_hi + 8 * c, hi);
+        umma::tmem_st8(ta_lo + 8 * c, lo);
+    }
+    return sc;
+}
+// Convenience: unscaled input, returns 1/scale for the epilogue.
+template <class F>
+__device__ __forceinline__ float encode_row(F&& f, uint32_t ta_hi, uint32_t ta_lo) {
+    const float sc = encode_row_s(f, ta_hi, ta_lo, 1.0f);
+    return sc == 1.0f ? 1.0f : 1.0f / sc;
+}
+
+}  // namespace tc16
+}  // namespace degnn

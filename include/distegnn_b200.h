@@ -218,6 +218,16 @@ DISTEGNN_API int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, i
                             const float *next_layer_params, float *h_out, float *x4_out, float *P,
                             float *Q, float *Hn, float *node_loc_out, float *vsum, void *stream);
 
+/* fp32-FMA twin of distegnn_node_layer_fwd (cross-check only). */
+DISTEGNN_API int distegnn_node_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                                              const int32_t *rowptr, const int32_t *batch32, const float *h,
+                                              const float *x4, const float *node_vel, const float *node_attr,
+                                              const float *agg_m, const float *agg_x, const float *agg_v,
+                                              const float *trans_v, const float *layer_params,
+                                              const float *next_layer_params, float *h_out, float *x4_out,
+                                              float *P, float *Q, float *Hn, float *node_loc_out, float *vsum,
+                                              void *stream);
+
 /* ---- virtual-node update (after the all-reduce of vsum) ------------------------------------------
  * The global halves of coord_model_virtual / node_model_virtual and the next layer's m_X
  * (FastEGNN.py:199, 229-233, 258-264) from the *summed* statistics (weighted_average_reduce,

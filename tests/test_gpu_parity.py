@@ -194,6 +194,67 @@ def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
             assert err <= 2e-5, (name, err)
 
 
+@pytest.mark.parametrize("Na,B,big", [(2, 1, False), (0, 9, False), (2, 1, True)])
+def test_node_kernel_tensor_core_vs_fma_twin(Na, B, big):
+    """tcgen05 node-update kernel against its fp32-FMA twin: single graph / batch with straddling tiles, with and
+    without node attributes, last-layer mode, and (big) features far outside the fp16 range."""
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    N, C = 70_001, 5
+    d = dev()
+    g = torch.Generator().manual_seed(Na + B)
+    sd = orc.init_state_dict(3, Na, 2, 64, C, 2, seed=8, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=Na, edge_attr_nf=2, virtual_channels=C, n_layers=2), sd)
+    lps = m._packed_params(d)["layers"]
+    R = lambda *s: torch.randn(*s, generator=g).to(d)
+    batch = torch.sort(torch.randint(0, B, (N,), generator=g))[0].to(torch.int32).to(d)
+    deg = torch.randint(0, 30, (N,), generator=g)
+    rowptr = torch.zeros(N + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
+    rowptr = rowptr.to(d)
+    h, agg_m, agg_v, vel, attr = R(N, 64), R(N, 64) * 5, R(N, 64), R(N, 3), (R(N, Na) if Na else None)
+    if big:
+        sc = torch.where(torch.rand(N, generator=g) < 0.03, 10 ** (3 + 3 * torch.rand(N, generator=g)),
+                         torch.ones(N)).to(d)
+        h, agg_m = h * sc[:, None], agg_m * sc[:, None]
+    x4, agg_x, trans_v = torch.zeros(N, 4, device=d), torch.zeros(N, 4, device=d), torch.zeros(N, 4, device=d)
+    x4[:, :3], agg_x[:, :3], trans_v[:, :3] = R(N, 3), R(N, 3), R(N, 3)
+    K = 4 + 3 * C + 64 * C
+    for flags in (0, _lib.FLAG_LAST):
+        outs = []
+        for fn in (be.node_layer_simt, be.node_layer):
+            new = lambda *s: torch.zeros(*s, device=d)
+            h2, x42, P2, Q2, Hn2, loc, vsum = new(N, 64), new(N, 4), new(N, 64), new(N, 64), new(N, 64), new(N, 3), new(B, K)
+            last = bool(flags)
+            fn((N, B, 2, C, Na), flags, rowptr, batch, h, x4, vel, attr, None if last else agg_m, agg_x,
+               None if last else agg_v, trans_v, lps[0], None if last else lps[1], None if last else h2, x42,
+               None if last else P2, None if last else Q2, None if last else Hn2, loc if last else None, vsum)
+            torch.cuda.synchronize()
+            outs.append(dict(h2=h2, x=x42[:, :3], P=P2, Q=Q2, Hn=Hn2, loc=loc, vsum=vsum[:, :4]))
+        if big:      # fp64 restatement of the stage: rows differ by 6 orders of magnitude, heads cancel heavily
+            D = lambda t_: None if t_ is None else t_.double()
+            z = lambda *s_: torch.zeros(*s_, device=d, dtype=torch.float64)
+            h2, x42, P2, Q2, Hn2, loc, vsum = z(N, 64), z(N, 4), z(N, 64), z(N, 64), z(N, 64), z(N, 3), z(B, K)
+            last = bool(flags)
+            ShadowBackend().node_layer((N, B, 2, C, Na), flags, rowptr, batch, D(h), D(x4), D(vel), D(attr),
+                                       None if last else D(agg_m), D(agg_x), None if last else D(agg_v), D(trans_v),
+                                       lps[0].double(), None if last else lps[1].double(), h2, x42, P2, Q2, Hn2,
+                                       loc if last else None, vsum)
+            ref64 = dict(h2=h2, x=x42[:, :3], P=P2, Q=Q2, Hn=Hn2, loc=loc, vsum=vsum[:, :4])
+        for k in outs[0]:
+            if big:
+                r = ref64[k]
+                rw = lambda o: float(((o.double() - r).abs().amax(1) / r.abs().amax(1).clamp(min=1e-6)).max())
+                e_fma, e_tc = rw(outs[0][k]), rw(outs[1][k])
+                print(f"Na={Na} B={B} big flags={flags} {k}: row-wise rel err vs fp64: fp32-FMA {e_fma:.3e}  tensor-core {e_tc:.3e}")
+                assert e_tc <= max(8 * e_fma, 2e-5) and e_tc <= 2e-3, (k, e_fma, e_tc)
+            else:
+                ref, got = outs[0][k], outs[1][k]
+                err = max_abs(got, ref) / max(1e-9, float(ref.abs().max()))
+                print(f"Na={Na} B={B} flags={flags} {k}: rel err {err:.3e}")
+                assert err <= 2e-5, (k, err)
+
+
 @pytest.mark.parametrize("name", SINGLE_CASES)
 def test_golden_fixtures(name):
     z, kw, sd = load_golden(name)
