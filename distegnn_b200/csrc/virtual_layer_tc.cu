@@ -1,5 +1,5 @@
-// Real<->virtual stage on the tensor cores (tcgen05 + TMEM) — production kernel behind
-// distegnn_virtual_layer_fwd.  Same math/outputs as virtual_layer.cu (kept as ..._simt for cross-checks);
+// Real<->virtual stage on the tensor cores with the 3xTF32 split (earlier production kernel, now
+// distegnn_virtual_layer_fwd_tf32: A/B timing and a third independent implementation for cross-checks).  Same math/outputs as virtual_layer.cu (kept as ..._simt for cross-checks);
 // replaces reference models/FastEGNN.py:252-253,154-163,180,191-193,207,220-223 and the global_mean_pool
 // scatters at :193,:222.
 //
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) virtual_layer_tc_kernel(const V
 
 }  // namespace degnn
 
-extern "C" int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+extern "C" int distegnn_virtual_layer_fwd_tf32(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
                                           const int32_t* batch32, const float* x4, const float* Hn,
                                           const float* Xv, const float* G, const float* layer_params,
                                           float* agg_v, float* trans_v, float* vsum, void* stream) {

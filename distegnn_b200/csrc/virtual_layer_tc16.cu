@@ -1,0 +1,349 @@
+// Real<->virtual stage on the tensor cores — production kernel behind distegnn_virtual_layer_fwd.
+// Replaces reference models/FastEGNN.py:252-253 (virtual geometry), 154-163 (edge_mode_virtual), 180, 191-193,
+// 207, 220-223 (virtual halves of coord_model_vel / coord_model_virtual / node_model / node_model_virtual) and
+// the global_mean_pool scatters at :193,:222.  Same math/outputs as virtual_layer.cu (fp32-FMA twin) and
+// virtual_layer_tc.cu (3xTF32 twin).
+//
+// Rows of a tile are (node, channel) pairs: TN = 128 / C nodes per tile, row = n_local*C + c, one TMEM lane per
+// row.  One CTA per SM, 512 threads = 4 independent tile groups of 4 warps; thread r of a group owns row r.
+// All three 64x64 layers run as kind::f16 tile GEMMs with the fp16 2-term split (tc16.cuh); TMEM per group:
+// A_hi 32 + A_lo 32 + D 64 columns (the two coordinate heads reuse D one after the other).
+//   stage 1  a1 = SiLU(Hn[node] + G[graph,c] + w_r·‖ΔX‖)  -> A              MMA 1: D = a1·W2vᵀ
+//   stage 2  mv = SiLU(D + b2v) -> shared tile + A                            MMA 2: D = mv·Wxvᵀ
+//            (while it runs: agg_v[node] = mean_c mv, per-graph Σ_i mv accumulated in shared memory)
+//   stage 3a φ_xv = w3xv·SiLU(D + bxv)                                        MMA 3: D = mv·WXᵀ
+//   stage 3b φ_X  = w3x·SiLU(D + bx);  trans_v[node] = mean_c(−ΔX·φ_xv);  per-graph Σ_i ΔX·φ_X accumulated.
+#include "common.cuh"
+#include "tc16.cuh"
+#include "umma.cuh"
+
+namespace degnn {
+
+struct VirtT16Args {
+    int64_t N;
+    int B, C;
+    unsigned flags;
+    const int32_t* batch;
+    const float* x4;
+    const float* Hn;
+    const float* Xv;
+    const float* G;
+    const float* w1r;
+    const float* w2; const float* b2;
+    const float* wxv; const float* bxv; const float* w3xv;
+    const float* wx; const float* bx; const float* w3x;
+    float* agg_v;
+    float* trans_v;
+    float* vsum;
+};
+
+constexpr int V16_THREADS = 512, V16_GROUPS = 4, V16_GROUP = 128;
+constexpr int V16_ROW = 68;
+constexpr int V16_MAXC = DISTEGNN_MAX_CHANNELS;
+constexpr int V16_W = 4096;
+constexpr int V16_SMEM_BYTES = 6 * V16_W * 2                           // W2v, Wxv, WX (hi+lo)
+                               + V16_GROUPS * TILE_M * V16_ROW * 4     // mv tile per group
+                               + V16_GROUPS * V16_MAXC * H * 4         // Σ mv accumulators per group
+                               + V16_GROUPS * 4 * V16_MAXC * 4         // Σ ΔX·φ_X accumulators per group
+                               + 6 * H * 4                             // w1r, b2v, bxv, w3xv, bx, w3x
+                               + V16_GROUPS * TILE_M * 4 * 4           // ΔX per row
+                               + V16_GROUPS * 2 * TILE_M * 4           // φ_xv, φ_X per row
+                               + V16_GROUPS * TILE_M * 4               // graph id per local node
+                               + 128;
+constexpr uint32_t V16_LBO = 1024;
+
+__global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const VirtT16Args a) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __half* W2hi = reinterpret_cast<__half*>(smem_raw);
+    __half* W2lo = W2hi + V16_W;
+    __half* Wxvhi = W2lo + V16_W;
+    __half* Wxvlo = Wxvhi + V16_W;
+    __half* Wxhi = Wxvlo + V16_W;
+    __half* Wxlo = Wxhi + V16_W;
+    float* tiles = reinterpret_cast<float*>(Wxlo + V16_W);
+    float* accH_all = tiles + V16_GROUPS * TILE_M * V16_ROW;
+    float* accX_all = accH_all + V16_GROUPS * V16_MAXC * H;
+    float* w1rs = accX_all + V16_GROUPS * 4 * V16_MAXC;
+    float* b2s = w1rs + H;
+    float* bxvs = b2s + H;
+    float* w3xvs = bxvs + H;
+    float* bxs = w3xvs + H;
+    float* w3xs = bxs + H;
+    float* dX_all = w3xs + H;
+    float* phi_all = dX_all + V16_GROUPS * TILE_M * 4;
+    int* sgraph_all = reinterpret_cast<int*>(phi_all + V16_GROUPS * 2 * TILE_M);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sgraph_all + V16_GROUPS * TILE_M);
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + V16_GROUPS);
+
+    const int tid = threadIdx.x;
+    const int grp = tid >> 7, t = tid & 127, wq = (tid >> 5) & 3;
+    const int C = a.C;
+    const int K = 4 + 3 * C + H * C;
+    const bool need_feat = !(a.flags & DISTEGNN_FLAG_LAST);
+    const int TN = TILE_M / C;
+
+    // ---- one-time setup ---------------------------------------------------------------------------
+    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, V16_THREADS);
+    tc16::stage_weight(Wxvhi, Wxvlo, a.wxv, 0, 64, tid, V16_THREADS);
+    tc16::stage_weight(Wxhi, Wxlo, a.wx, 0, 64, tid, V16_THREADS);
+    if (tid < H) {
+        w1rs[tid] = a.w1r[tid];
+        b2s[tid] = a.b2[tid];
+        bxvs[tid] = a.bxv[tid];
+        w3xvs[tid] = a.w3xv[tid];
+        bxs[tid] = a.bx[tid];
+        w3xs[tid] = a.w3x[tid];
+    }
+    for (int i = tid; i < V16_GROUPS * (V16_MAXC * H + 4 * V16_MAXC); i += V16_THREADS) accH_all[i] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < V16_GROUPS; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if ((tid >> 5) == 0) tmem_alloc(tmem_base_s, 512);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    const uint32_t tbase = *tmem_base_s;
+    const uint32_t lane_off = ((uint32_t)(32 * wq)) << 16;
+    const uint32_t col0 = tbase + (uint32_t)grp * 128u;
+    const uint32_t tA_hi = col0, tA_lo = col0 + 32, tD = col0 + 64;
+    const uint32_t idesc = make_idesc_f16(128, 64, 0, 0);
+    auto desc = [&](const __half* p) { return make_b_desc(smem_u32(p), V16_LBO, 128); };
+    const uint64_t dW2hi = desc(W2hi), dW2lo = desc(W2lo), dWxvhi = desc(Wxvhi), dWxvlo = desc(Wxvlo),
+                   dWxhi = desc(Wxhi), dWxlo = desc(Wxlo);
+    float* tile_s = tiles + grp * TILE_M * V16_ROW;
+    float* myrow = tile_s + t * V16_ROW;
+    float* accH = accH_all + grp * V16_MAXC * H;
+    float* accX = accX_all + grp * 4 * V16_MAXC;
+    float* dXs = dX_all + grp * TILE_M * 4;
+    float* phis = phi_all + grp * 2 * TILE_M;
+    int* sgraph = sgraph_all + grp * TILE_M;
+    uint64_t* mbar = bars + grp;
+    const uint32_t bar_id = 1 + grp;
+    uint32_t mph = 0;
+    int cur_graph = -1;
+
+    auto flush = [&](int g) {                      // all threads of the group
+        if (g >= 0) {
+            float* dst = a.vsum + (size_t)g * K;
+            if (need_feat)
+                for (int i = t; i < C * H; i += V16_GROUP) {
+                    atomicAdd(dst + 4 + 3 * C + i, accH[i]);
+                    accH[i] = 0.f;
+                }
+            if (t < 3 * C) {
+                atomicAdd(dst + 4 + t, accX[t]);
+                accX[t] = 0.f;
+            }
+        }
+    };
+    auto a_ready = [&]() {
+        wait_st();
+        fence_before_sync();
+        named_bar(bar_id, V16_GROUP);
+    };
+    auto issue = [&](uint64_t bhi, uint64_t blo) {
+        if (t == 0) {
+            fence_after_sync();
+            tc16::issue_f16x3<V16_LBO>(tD, tA_hi, tA_lo, bhi, blo, idesc, false);
+            mma_commit(mbar);
+        }
+        __syncwarp();
+    };
+    auto mma_done = [&]() {
+        mbar_wait(mbar, mph);
+        mph ^= 1;
+        __syncwarp();
+        fence_after_sync();
+    };
+
+    const int64_t num_tiles = (a.N + TN - 1) / TN;
+    for (int64_t tile = (int64_t)blockIdx.x * V16_GROUPS + grp; tile < num_tiles; tile += (int64_t)gridDim.x * V16_GROUPS) {
+        const int64_t n0 = tile * TN;
+        const int nvalid = (int)min((int64_t)TN, a.N - n0);
+        const int rows = nvalid * C;
+        if (t < TN) sgraph[t] = (t < nvalid) ? __ldg(a.batch + n0 + t) : -1;
+        named_bar(bar_id, V16_GROUP);
+        const int g_first = sgraph[0], g_last = sgraph[nvalid - 1];
+        const bool single = (g_first == g_last);
+        if (single && g_first != cur_graph) {
+            flush(cur_graph);
+            cur_graph = g_first;
+            named_bar(bar_id, V16_GROUP);
+        }
+
+        // ---- stage 1 ------------------------------------------------------------------------------
+        const bool rvalid = t < rows;
+        const int nl = rvalid ? t / C : 0;
+        const int ch = rvalid ? t - nl * C : 0;
+        const int g = rvalid ? sgraph[nl] : g_first;
+        const size_t node = (size_t)(n0 + nl);
+        float vr;
+        {
+            const float4 xi = ldg4(a.x4 + node * 4);
+            const float* Xg = a.Xv + (size_t)g * 3 * C;
+            const float dx = __ldg(Xg + ch) - xi.x, dy = __ldg(Xg + C + ch) - xi.y, dz = __ldg(Xg + 2 * C + ch) - xi.z;
+            vr = sqrtf(dx * dx + dy * dy + dz * dz);
+            *reinterpret_cast<float4*>(dXs + 4 * t) = make_float4(dx, dy, dz, 0.f);
+        }
+        const float* hrow = a.Hn + node * H;
+        const float* grow = a.G + ((size_t)g * C + ch) * H;
+        const float inv1 = tc16::encode_row(
+            [&](int c, float (&v)[16], bool) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cc = 16 * c + 4 * j4;
+                    float4 pre = silu4(fma4(vr, *reinterpret_cast<const float4*>(w1rs + cc), add4(ldg4(hrow + cc), ldg4(grow + cc))));
+                    if (!rvalid) pre = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * j4 + 0] = pre.x; v[4 * j4 + 1] = pre.y; v[4 * j4 + 2] = pre.z; v[4 * j4 + 3] = pre.w;
+                }
+            },
+            lane_off + tA_hi, lane_off + tA_lo);
+        a_ready();
+        issue(dW2hi, dW2lo);
+        mma_done();
+
+        // ---- stage 2: mv = SiLU(D + b2v) -> shared tile and A ---------------------------------------------
+        const float inv2 = tc16::encode_row(
+            [&](int c, float (&v)[16], bool first) {
+                uint32_t d[16];
+                tmem_ld16(lane_off + tD + 16 * c, d);
+                wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cc = 16 * c + 4 * j4;
+                    const float4 bb = *reinterpret_cast<const float4*>(b2s + cc);
+                    float4 m;
+                    m.x = silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv1, bb.x));
+                    m.y = silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv1, bb.y));
+                    m.z = silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv1, bb.z));
+                    m.w = silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv1, bb.w));
+                    if (first && need_feat) *reinterpret_cast<float4*>(myrow + cc) = m;
+                    v[4 * j4 + 0] = m.x; v[4 * j4 + 1] = m.y; v[4 * j4 + 2] = m.z; v[4 * j4 + 3] = m.w;
+                }
+            },
+            lane_off + tA_hi, lane_off + tA_lo);
+        a_ready();
+        issue(dWxvhi, dWxvlo);
+        // pools of mv while MMA 2 runs
+        if (need_feat) {
+            const int c64 = t & 63, q2 = t >> 6;
+            const float invC = 1.0f / (float)C;
+            for (int n = q2; n < nvalid; n += 2) {          // mean over channels per node
+                float s = 0.f;
+                for (int c = 0; c < C; ++c) s += tile_s[(n * C + c) * V16_ROW + c64];
+                a.agg_v[(size_t)(n0 + n) * H + c64] = s * invC;
+            }
+            if (single) {                                    // sum over nodes per channel
+                for (int c = q2; c < C; c += 2) {
+                    float s = 0.f;
+                    for (int n = 0; n < nvalid; ++n) s += tile_s[(n * C + c) * V16_ROW + c64];
+                    accH[c * H + c64] += s;
+                }
+            } else {
+                for (int n = q2; n < nvalid; n += 2) {
+                    float* dst = a.vsum + (size_t)sgraph[n] * K + 4 + 3 * C;
+                    for (int c = 0; c < C; ++c) atomicAdd(dst + c * H + c64, tile_s[(n * C + c) * V16_ROW + c64]);
+                }
+            }
+        }
+        mma_done();
+
+        // ---- stage 3a: φ_xv = w3xv·SiLU(D + bxv) --------------------------------------------------------
+        auto head = [&](const float* bs, const float* ws) {
+            float phi = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t d[16];
+                tmem_ld16(lane_off + tD + 16 * c, d);
+                wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cc = 16 * c + 4 * j4;
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + cc);
+                    const float4 ww = *reinterpret_cast<const float4*>(ws + cc);
+                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv2, bb.x)), ww.x, phi);
+                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv2, bb.y)), ww.y, phi);
+                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv2, bb.z)), ww.z, phi);
+                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv2, bb.w)), ww.w, phi);
+                }
+            }
+            return phi;
+        };
+        phis[t] = head(bxvs, w3xvs);
+        fence_before_sync();
+        named_bar(bar_id, V16_GROUP);                  // D fully read (A still holds mv)
+        issue(dWxhi, dWxlo);
+        // trans_v[node] = mean_c(−ΔX_c·φ_xv,c) while MMA 3 runs
+        for (int i = t; i < nvalid * 3; i += V16_GROUP) {
+            const int n = i / 3, d = i - 3 * n;
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s = fmaf(-dXs[4 * (n * C + c) + d], phis[n * C + c], s);
+            a.trans_v[(size_t)(n0 + n) * 4 + d] = s / (float)C;
+        }
+        mma_done();
+
+        // ---- stage 3b: φ_X = w3x·SiLU(D + bx); Σ_i ΔX_ic·φ_X,ic per graph [3][C] -----------------------------
+        phis[TILE_M + t] = head(bxs, w3xs);
+        fence_before_sync();
+        named_bar(bar_id, V16_GROUP);
+        if (t < 3 * C) {
+            const int d = t / C, c = t - d * C;
+            const float* phx = phis + TILE_M;
+            if (single) {
+                float s = 0.f;
+                for (int n = 0; n < nvalid; ++n) s = fmaf(dXs[4 * (n * C + c) + d], phx[n * C + c], s);
+                accX[t] += s;
+            } else {
+                for (int n = 0; n < nvalid; ++n)
+                    atomicAdd(a.vsum + (size_t)sgraph[n] * K + 4 + t, dXs[4 * (n * C + c) + d] * phx[n * C + c]);
+            }
+        }
+        named_bar(bar_id, V16_GROUP);                  // sgraph/dXs/phis/tile_s are rewritten by the next tile
+    }
+    flush(cur_graph);
+
+    fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace degnn
+
+extern "C" int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                                          const int32_t* batch32, const float* x4, const float* Hn,
+                                          const float* Xv, const float* G, const float* layer_params,
+                                          float* agg_v, float* trans_v, float* vsum, void* stream) {
+    using namespace degnn;
+    if (int rc = check_dims(A, C, Na)) return rc;
+    if (n_nodes == 0) return DISTEGNN_OK;
+    DEGNN_CHECK_ARG(n_nodes > 0 && n_graphs > 0, "bad size");
+    DEGNN_CHECK_ARG(batch32 && x4 && Hn && Xv && G && layer_params && trans_v && vsum, "null pointer");
+    DEGNN_CHECK_ARG((flags & DISTEGNN_FLAG_LAST) || agg_v, "null agg_v");
+    Layout L = make_layout(A, C, Na);
+    VirtT16Args a;
+    a.N = n_nodes; a.B = n_graphs; a.C = C; a.flags = flags;
+    a.batch = batch32; a.x4 = x4; a.Hn = Hn; a.Xv = Xv; a.G = G;
+    a.w1r = layer_params + L.off[DISTEGNN_P_V_W1R];
+    a.w2 = layer_params + L.off[DISTEGNN_P_V_W2];
+    a.b2 = layer_params + L.off[DISTEGNN_P_V_B2];
+    a.wxv = layer_params + L.off[DISTEGNN_P_V_WXV];
+    a.bxv = layer_params + L.off[DISTEGNN_P_V_BXV];
+    a.w3xv = layer_params + L.off[DISTEGNN_P_V_W3XV];
+    a.wx = layer_params + L.off[DISTEGNN_P_V_WX];
+    a.bx = layer_params + L.off[DISTEGNN_P_V_BX];
+    a.w3x = layer_params + L.off[DISTEGNN_P_V_W3X];
+    a.agg_v = agg_v; a.trans_v = trans_v; a.vsum = vsum;
+    cudaFuncSetAttribute(virtual_layer_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V16_SMEM_BYTES);
+    const int TN = TILE_M / C;
+    const int64_t tiles = (n_nodes + TN - 1) / TN;
+    int64_t grid = (tiles + V16_GROUPS - 1) / V16_GROUPS;
+    if (grid > sm_count()) grid = sm_count();
+    virtual_layer_t16_kernel<<<(unsigned)grid, V16_THREADS, V16_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    DEGNN_CHECK_LAUNCH();
+    return DISTEGNN_OK;
+}

@@ -195,6 +195,13 @@ DISTEGNN_API int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A
                                const float *Xv, const float *G, const float *layer_params,
                                float *agg_v, float *trans_v /*[N,4]*/, float *vsum, void *stream);
 
+/* 3xTF32 tensor-core twin of distegnn_virtual_layer_fwd (cross-check / A-B timing only). */
+DISTEGNN_API int distegnn_virtual_layer_fwd_tf32(int64_t n_nodes, int n_graphs, int A, int C, int Na,
+                                                 unsigned flags, const int32_t *batch32, const float *x4,
+                                                 const float *Hn, const float *Xv, const float *G,
+                                                 const float *layer_params, float *agg_v, float *trans_v,
+                                                 float *vsum, void *stream);
+
 /* fp32-FMA twin of distegnn_virtual_layer_fwd (cross-check only). */
 DISTEGNN_API int distegnn_virtual_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na,
                                                  unsigned flags, const int32_t *batch32, const float *x4,

@@ -182,16 +182,17 @@ def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
     K = 4 + 3 * C + 64 * C
     for flags in (0, _lib.FLAG_LAST):
         outs = []
-        for fn in (be.virtual_layer, be.virtual_layer_simt):
+        for fn in (be.virtual_layer_simt, be.virtual_layer, be.virtual_layer_tf32):
             agg_v, trans_v = torch.zeros(N, 64, device=d), torch.zeros(N, 4, device=d)
             vsum = torch.zeros(B, K, device=d)
             fn((N, B, 2, C, 0), flags, batch, x4, Hn, Xv, G, lp, None if flags else agg_v, trans_v, vsum)
             torch.cuda.synchronize()
             outs.append((agg_v, trans_v[:, :3], vsum))
-        for name, x, y in zip(("agg_v", "trans_v", "vsum"), outs[0], outs[1]):
-            err = max_abs(x, y) / max(1e-9, float(y.abs().max()))
-            print(f"C={C} B={B} flags={flags} {name}: rel err {err:.3e}")
-            assert err <= 2e-5, (name, err)
+        for impl, o in (("fp16-split", outs[1]), ("3xTF32", outs[2])):
+            for name, x, y in zip(("agg_v", "trans_v", "vsum"), o, outs[0]):
+                err = max_abs(x, y) / max(1e-9, float(y.abs().max()))
+                print(f"C={C} B={B} flags={flags} {impl} {name}: rel err {err:.3e}")
+                assert err <= 2e-5, (impl, name, err)
 
 
 @pytest.mark.parametrize("Na,B,big", [(2, 1, False), (0, 9, False), (2, 1, True)])
