@@ -35,7 +35,8 @@ def _deps_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [NVCC, *ARCH, *CFLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("DISTEGNN_NVCC_DEFS", "").split()      # e.g. "-DT16_CHUNK_UNROLL=4" for A/B builds
+    cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")

@@ -46,6 +46,9 @@ int sm_count();   // cached multiprocessor count of the current device
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float silu(float x) {
+#ifdef DEGNN_DIAG_NO_SILU      // diagnostic build only (timing apportionment): NOT the model's activation
+    return x * 0.5f;
+#endif
     // x·σ(x) = x · rcp(1 + 2^{-x·log2 e}): FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL — no range fix-ups needed:
     // x → −∞ gives 2^{+big} = inf, rcp(inf) = 0, x·0 = −0;  x → +∞ gives rcp(1) = 1.  |rel err| ≲ 5e-7.
     float e, r;

@@ -54,9 +54,14 @@ constexpr int T16_SMEM_BYTES = 4 * T16_W_HALFS * 2        // W2 hi/lo, Wc hi/lo
                                + T16_GROUPS * T16_QBUF * 4
                                + (4 * H + DISTEGNN_MAX_EDGE_ATTR * H) * 4   // b2, bc, w3, w1r, w1e
                                + T16_GROUPS * TILE_M * 4  // srow
+                               + T16_GROUPS * 4 * 4       // run-start bit masks (one word per warp)
                                + 128;                     // mbarriers + tmem base
 constexpr uint32_t T16_LBO = 1024, T16_SBO = 128;         // fp16 K-major no-swizzle: 8 rows x 8 halfs per core matrix
 constexpr float T16_RANGE = 3.0e4f;
+#ifndef T16_CHUNK_UNROLL
+#define T16_CHUNK_UNROLL 2     // chunks (of 16 columns) unrolled per stage loop: trades code size (I-cache) for ILP
+#endif
+constexpr int kChunkUnroll = T16_CHUNK_UNROLL;
 
 // weight W[n][k] = wt_kmajor[k*64+n] -> fp16 hi/lo at (k/8)*512 + (n/8)*64 + (n%8)*8 + k%8 (in halfs)
 __device__ __forceinline__ void stage_weight_f16(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int tid,
@@ -125,7 +130,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
     float* w1rs = w3s + H;
     float* w1es = w1rs + H;
     int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);   // [4][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(srow_all + T16_GROUPS * TILE_M);  // [4][2]
+    uint32_t* rmask_all = reinterpret_cast<uint32_t*>(srow_all + T16_GROUPS * TILE_M);   // [4][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rmask_all + T16_GROUPS * 4);      // [4][2]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * T16_GROUPS);
 
     const int tid = threadIdx.x;
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
     float* qb = qbufs + grp * T16_QBUF;
     float* myq = qb + t * T16_QROW;
     int* srow = srow_all + grp * TILE_M;
+    uint32_t* rmask = rmask_all + grp * 4;
     uint64_t* qbar = bars + grp * 2;
     uint64_t* mbar = bars + grp * 2 + 1;
     const uint32_t bar_id = 1 + grp;
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         float inv_s1 = 1.0f;
         {
             __half2 mx = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
+#pragma unroll kChunkUnroll
             for (int c = 0; c < 4; ++c) {
                 float v[16];
                 uint32_t hi[8], lo[8];
@@ -281,6 +288,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
             issue_gemm_f16x3(tD, tA_hi, tA_lo, dW2hi, dW2lo, idesc, mbar);
         }
         __syncwarp();
+        {   // bit i of rmask[w] = edge 32w+i starts a new run of equal destination rows (read after barrier 2)
+            const int prev = t > 0 ? srow[t - 1] : -2;
+            const uint32_t starts = __ballot_sync(FULL, prev != row_c);
+            if (lane == 0) rmask[wq] = starts;
+        }
         int row_n, rr_n, col_n;
         float ea_n[AMAX];
         load_edge(tile + stride, row_n, rr_n, col_n, ea_n);
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         float inv_s2 = 1.0f;
         {
             __half2 mx = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
+#pragma unroll kChunkUnroll
             for (int c = 0; c < 4; ++c) {
                 float v[16];
                 uint32_t hi[8], lo[8];
@@ -354,23 +366,47 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
             issue_gemm_f16x3(tD, tA_hi, tA_lo, dWchi, dWclo, idesc, mbar);
         }
         __syncwarp();
+#ifdef DEGNN_DIAG_NO_SEGSUM
+        if (false) {
+#else
         if (need_m) {
-            // thread (column c, half of the tile): runs of equal destination row -> one RED per (run, column)
-            const int c = t & 63, eb = (t >> 6) * 64;
+#endif
+            // thread (column c, half of the tile): one RED per (run of equal destination row, column)
+            const int c = t & 63, hh = t >> 6, eb = hh * 64;
             const float* colp = qb + eb * T16_QROW + c;
-            int cur = srow[eb];
-            float s = 0.f;
-#pragma unroll 8
-            for (int e = 0; e < 64; ++e) {
-                const int r = srow[eb + e];
-                if (r != cur) {
-                    if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s);
-                    s = 0.f;
-                    cur = r;
+            uint64_t M = ((uint64_t)rmask[2 * hh + 1] << 32) | rmask[2 * hh] | 1ull;   // run starts in this half
+            if (__popcll(M) <= 24) {
+                // few runs (the usual radius-graph regime): walk run by run, 2 instructions per edge
+                while (M) {
+                    const int e0 = __ffsll((long long)M) - 1;
+                    M &= M - 1;
+                    const int e1 = M ? __ffsll((long long)M) - 1 : 64;
+                    float s0 = 0.f, s1 = 0.f;
+                    int e = e0;
+                    for (; e + 1 < e1; e += 2) {
+                        s0 += colp[e * T16_QROW];
+                        s1 += colp[(e + 1) * T16_QROW];
+                    }
+                    if (e < e1) s0 += colp[e * T16_QROW];
+                    const int r = srow[eb + e0];
+                    if (r >= 0) atomicAdd(a.agg_m + (size_t)r * H + c, s0 + s1);
                 }
-                s += colp[e * T16_QROW];
+            } else {
+                // many short runs (sparse partitions): per-edge walk
+                int cur = srow[eb];
+                float s0 = 0.f;
+#pragma unroll 4
+                for (int e = 0; e < 64; ++e) {
+                    const int r0 = srow[eb + e];
+                    if (r0 != cur) {
+                        if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s0);
+                        s0 = 0.f;
+                        cur = r0;
+                    }
+                    s0 += colp[e * T16_QROW];
+                }
+                if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s0);
             }
-            if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s);
             fence_proxy_async_smem();          // generic accesses to qb ordered before the TMA refill below
         }
         named_bar(bar_id, T16_GROUP);          // whole group done with the staging buffer
@@ -381,8 +417,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         fence_after_sync();
 
         // ---- stage 3: φ = w3·SiLU(D/s + bc); Δx·φ summed per destination row --------------------------------
-        float phi = 0.f;
-#pragma unroll
+        float ph0 = 0.f, ph1 = 0.f, ph2 = 0.f, ph3 = 0.f;      // four independent FMA chains
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c) {
             uint32_t d[16];
             tmem_ld16(lane_off + tD + 16 * c, d);
@@ -392,12 +428,13 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
                 const int cc = 16 * c + 4 * j4;
                 const float4 bb = *reinterpret_cast<const float4*>(bcs + cc);
                 const float4 ww = *reinterpret_cast<const float4*>(w3s + cc);
-                phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv_s2, bb.x)), ww.x, phi);
-                phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv_s2, bb.y)), ww.y, phi);
-                phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv_s2, bb.z)), ww.z, phi);
-                phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv_s2, bb.w)), ww.w, phi);
+                ph0 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv_s2, bb.x)), ww.x, ph0);
+                ph1 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv_s2, bb.y)), ww.y, ph1);
+                ph2 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv_s2, bb.z)), ww.z, ph2);
+                ph3 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv_s2, bb.w)), ww.w, ph3);
             }
         }
+        const float phi = (ph0 + ph1) + (ph2 + ph3);
         fence_before_sync();                   // D reads ordered before the next tile's MMA 1
         {
             float sx = dx * phi, sy = dy * phi, sz = dz * phi;

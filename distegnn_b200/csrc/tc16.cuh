@@ -16,6 +16,10 @@ namespace degnn {
 namespace tc16 {
 
 constexpr float RANGE = 3.0e4f;
+#ifndef TC16_CHUNK_UNROLL
+#define TC16_CHUNK_UNROLL 2    // chunks (of 16 columns) unrolled in encode_row: code size (I-cache) vs ILP
+#endif
+constexpr int kChunkUnroll = TC16_CHUNK_UNROLL;
 
 // stage W[n][k] (given k-major: wt[k*64+n]) as rows n_off..n_off+63 of an N_total-row B operand, fp16 hi/lo
 __device__ __forceinline__ void stage_weight(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int n_off,
@@ -82,7 +86,7 @@ __device__ __forceinline__ float encode_row_s(F&& f, uint32_t ta_hi, uint32_t ta
     __half2 mx = __floats2half2_rn(0.f, 0.f);
     const bool pre_scaled = __any_sync(FULL, s_in != 1.0f);
     if (!pre_scaled) {
-#pragma unroll
+#pragma unroll kChunkUnroll
         for (int c = 0; c < 4; ++c) {
             float v[16];
             uint32_t hi[8], lo[8];

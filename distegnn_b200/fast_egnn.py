@@ -115,7 +115,7 @@ class _GraphCache:
     def get(self, backend, edge_index: Tensor, n_nodes: int):
         key = id(edge_index)
         hit = self.entries.get(key)
-        if hit is not None and hit[0] is edge_index and hit[1] == edge_index._version and hit[2] == n_nodes:
+        if hit is not None and hit[0] is edge_index and hit[1] == edge_index._version and hit[2] == n_nodes:   # noqa: E501
             self.entries.move_to_end(key)
             return hit[3]
         ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
@@ -125,6 +125,18 @@ class _GraphCache:
         while len(self.entries) > self.capacity:
             self.entries.popitem(last=False)
         return csr
+
+    def sorted_edge_attr(self, backend, edge_index: Tensor, edge_attr: Tensor, perm: Tensor) -> Tensor:
+        """edge_attr permuted into CSR order, cached next to the CSR of `edge_index` while the SAME edge_attr
+        tensor (identity + in-place version) keeps being passed — the steady state of inference / rollouts."""
+        ent = self.entries.get(id(edge_index))
+        if ent is not None and ent[0] is edge_index and len(ent) == 6 and ent[4][0] is edge_attr \
+                and ent[4][1] == edge_attr._version:
+            return ent[5]
+        ea = backend.gather_rows(edge_attr.detach().to(torch.float32).contiguous(), perm)
+        if ent is not None and ent[0] is edge_index:
+            self.entries[id(edge_index)] = ent[:4] + ((edge_attr, edge_attr._version), ea)
+        return ea
 
 
 # --------------------------------------------------------------------------------------------------
@@ -246,7 +258,7 @@ class FastEGNN(nn.Module):
             pk = self._packed_params(dev)
             layers: List[Tensor] = pk["layers"]
             rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
-            ea = be.gather_rows(f32(edge_attr), perm) if A > 0 else None
+            ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
             node_feat, node_loc, node_vel = f32(node_feat), f32(node_loc), f32(node_vel)
             attr = f32(node_attr) if Na > 0 else None
             data_batch = data_batch.contiguous()

@@ -104,6 +104,24 @@ def test_graph_cache_reuse_and_invalidation():
         assert m._graphs.builds == 3
 
 
+def test_sorted_edge_attr_cache():
+    z, kw, sd = load_golden("fluid160_c5")
+    inp = golden_inputs(z)
+    m = make_model(kw, sd)
+    calls = []
+    orig = m._backend.gather_rows
+    m._backend.gather_rows = lambda src, perm: (calls.append(1), orig(src, perm))[1]
+    with torch.no_grad():
+        a, _ = m(**inp)
+        b, _ = m(**inp)
+        assert len(calls) == 1 and torch.equal(a, b)            # same edge_attr tensor: permuted once
+        inp["edge_attr"].mul_(2.0)                               # in-place change must invalidate
+        c, _ = m(**inp)
+        assert len(calls) == 2 and max_abs(a, c) > 0
+        m(**{**inp, "edge_attr": inp["edge_attr"].clone()})      # another tensor: permuted again
+        assert len(calls) == 3
+
+
 def test_weight_update_repacks():
     z, kw, sd = load_golden("fluid160_c5")
     inp = golden_inputs(z)
