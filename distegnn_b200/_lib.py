@@ -33,6 +33,7 @@ SIGNATURES = {
     "distegnn_build_csr": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "distegnn_gather_rows": [_vp, _vp, _i64, _i32, _vp, _vp],
     "distegnn_embed_fwd": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
+    "distegnn_embed_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
     "distegnn_edge_layer_fwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_edge_layer_fwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_edge_layer_fwd_tf32": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,

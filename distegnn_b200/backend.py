@@ -67,6 +67,15 @@ class CudaBackend:
                                           self._s(h)), "embed_fwd")
         self.launches += 1 if N else 0
 
+    def embed_simt(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
+                   Hn, vsum) -> None:
+        """fp32-FMA twin of embed (cross-check only)."""
+        N, B, F, A, Cn, Na = dims
+        check(self.lib.distegnn_embed_fwd_simt(N, B, F, A, Cn, Na, ptr(node_feat), ptr(node_loc),
+                                               ptr(data_batch), ptr(emb_wt), ptr(emb_b), ptr(layer0), ptr(h),
+                                               ptr(x4), ptr(batch32), ptr(P), ptr(Q), ptr(Hn), ptr(vsum),
+                                               self._s(h)), "embed_fwd_simt")
+
     def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
         N, E, A, Cn, Na = dims
         check(self.lib.distegnn_edge_layer_fwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
 // =================================================================================================
 // C ABI
 // =================================================================================================
-extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
+extern "C" int distegnn_embed_fwd_simt(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
                                   const float* node_feat, const float* node_loc,
                                   const int64_t* data_batch, const float* emb_wt, const float* emb_b,
                                   const float* layer0_params, float* h, float* x4, int32_t* batch32,

@@ -390,6 +390,186 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     if ((tid >> 5) == 0) tmem_dealloc(tbase, 512);
 }
 
+// =================================================================================================
+// embedding prologue on the tensor cores (FastEGNN.forward, reference models/FastEGNN.py:298-302):
+// h0 = embedding_in(node_feat) per node (F <= 16 inputs: plain FMAs), then P/Q/Hn of layer 0 as one N = 192
+// kind::f16 tile GEMM; also node_loc -> x4, data_batch -> int32, and Σ(x,1) per graph into vsum.
+// =================================================================================================
+struct EmbedTcArgs {
+    int64_t N;
+    int B, F, K;
+    const float* feat; const float* loc; const int64_t* batch64;
+    const float* wt; const float* bias;                                  // [F][64], [64]
+    const float* nw1a; const float* nxb1; const float* nw1b; const float* nw1h;
+    float* h; float* x4; int32_t* batch32; float* P; float* Q; float* Hn; float* vsum;
+};
+constexpr int ET_SMEM_BYTES = 2 * 3 * NT_W * 2 + (DISTEGNN_MAX_NODE_FEAT + 2) * H * 4 + NT_GROUPS * 8 * 4 + 64;
+
+__global__ void __launch_bounds__(NT_THREADS, 1) embed_tc_kernel(const EmbedTcArgs a) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __half* NXhi = reinterpret_cast<__half*>(smem_raw);
+    __half* NXlo = NXhi + 3 * NT_W;
+    float* wts = reinterpret_cast<float*>(NXlo + 3 * NT_W);     // [F][64]
+    float* bs = wts + DISTEGNN_MAX_NODE_FEAT * H;
+    float* nxb1s = bs + H;
+    float* acc_all = nxb1s + H;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(acc_all + NT_GROUPS * 8);
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + NT_GROUPS);
+    const int tid = threadIdx.x;
+    const int grp = tid >> 7, t = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
+    const int F = a.F;
+
+    tc16::stage_weight(NXhi, NXlo, a.nw1a, 0, 192, tid, NT_THREADS);
+    tc16::stage_weight(NXhi, NXlo, a.nw1b, 64, 192, tid, NT_THREADS);
+    tc16::stage_weight(NXhi, NXlo, a.nw1h, 128, 192, tid, NT_THREADS);
+    for (int i = tid; i < F * H; i += NT_THREADS) wts[i] = a.wt[i];
+    if (tid < H) {
+        bs[tid] = a.bias[tid];
+        nxb1s[tid] = a.nxb1[tid];
+    }
+    if (tid < NT_GROUPS * 8) acc_all[tid] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < NT_GROUPS; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if ((tid >> 5) == 0) tmem_alloc(tmem_base_s, 512);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    const uint32_t tbase = *tmem_base_s;
+    const uint32_t lane_off = ((uint32_t)(32 * wq)) << 16;
+    const uint32_t col0 = tbase + (uint32_t)grp * 256u;
+    const uint32_t tA_hi = col0, tA_lo = col0 + 32, tD1 = col0 + 64;
+    const uint32_t idesc192 = make_idesc_f16(128, 192, 0, 0);
+    const uint64_t dNXhi = make_b_desc(smem_u32(NXhi), NT_LBO192, 128), dNXlo = make_b_desc(smem_u32(NXlo), NT_LBO192, 128);
+    float* accS = acc_all + grp * 8;
+    int* sg = reinterpret_cast<int*>(accS + 4);
+    uint64_t* mbar = bars + grp;
+    const uint32_t bar_id = 1 + grp;
+    uint32_t mph = 0;
+    int cur_graph = -1, it = 0;
+
+    const int64_t num_tiles = (a.N + TILE_M - 1) / TILE_M;
+    for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < num_tiles; tile += (int64_t)gridDim.x * NT_GROUPS, ++it) {
+        int* sgp = sg + 2 * (it & 1);
+        const int64_t n0 = tile * TILE_M;
+        const int nvalid = (int)min((int64_t)TILE_M, a.N - n0);
+        const bool valid = t < nvalid;
+        const size_t node = (size_t)(n0 + (valid ? t : 0));
+        int g = -1;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float f[DISTEGNN_MAX_NODE_FEAT];
+#pragma unroll
+        for (int k = 0; k < DISTEGNN_MAX_NODE_FEAT; ++k) f[k] = (valid && k < F) ? __ldg(a.feat + node * F + k) : 0.f;
+        if (valid) {
+            g = (int)a.batch64[node];
+            a.batch32[node] = g;
+            const float* p = a.loc + node * 3;
+            xv = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+            *reinterpret_cast<float4*>(a.x4 + node * 4) = xv;
+        }
+        if (t == 0) sgp[0] = g;
+        if (t == nvalid - 1) sgp[1] = g;
+
+        // h0 row -> HBM and -> A
+        const float inv_n = tc16::encode_row(
+            [&](int c, float (&v)[16], bool first) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float z = bs[16 * c + j];
+#pragma unroll
+                    for (int k = 0; k < DISTEGNN_MAX_NODE_FEAT; ++k)
+                        if (k < F) z = fmaf(f[k], wts[k * H + 16 * c + j], z);
+                    v[j] = valid ? z : 0.f;
+                }
+                if (first && valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        *reinterpret_cast<float4*>(a.h + node * H + 16 * c + 4 * j4) =
+                            make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                }
+            },
+            lane_off + tA_hi, lane_off + tA_lo);
+        wait_st();
+        fence_before_sync();
+        named_bar(bar_id, NT_GROUP);
+        if (t == 0) {
+            fence_after_sync();
+            tc16::issue_f16x3<NT_LBO192>(tD1, tA_hi, tA_lo, dNXhi, dNXlo, idesc192, false);
+            mma_commit(mbar);
+        }
+        __syncwarp();
+        // Σ(x,1) per graph while the MMA runs
+        const int g_first = sgp[0];
+        const bool single = g_first == sgp[1];
+        if (single && g_first != cur_graph) {
+            if (cur_graph >= 0 && t < 4) {
+                atomicAdd(a.vsum + (size_t)cur_graph * a.K + t, accS[t]);
+                accS[t] = 0.f;
+            }
+            cur_graph = g_first;
+            named_bar(bar_id, NT_GROUP);
+        }
+        if (single) {
+            float s4[4] = {xv.x, xv.y, xv.z, valid ? 1.f : 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s4[j] += __shfl_xor_sync(FULL, s4[j], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(accS + j, s4[j]);
+            }
+        } else if (valid) {
+            float* dst = a.vsum + (size_t)g * a.K;
+            atomicAdd(dst + 0, xv.x);
+            atomicAdd(dst + 1, xv.y);
+            atomicAdd(dst + 2, xv.z);
+            atomicAdd(dst + 3, 1.0f);
+        }
+        mbar_wait(mbar, mph);
+        mph ^= 1;
+        __syncwarp();
+        fence_after_sync();
+#pragma unroll 1
+        for (int o = 0; o < 3; ++o) {
+            float* dst = (o == 0 ? a.P : (o == 1 ? a.Q : a.Hn)) + node * H;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t d[16];
+                tmem_ld16(lane_off + tD1 + 64 * o + 16 * c, d);
+                wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 r;
+                        r.x = __uint_as_float(d[4 * j4 + 0]) * inv_n;
+                        r.y = __uint_as_float(d[4 * j4 + 1]) * inv_n;
+                        r.z = __uint_as_float(d[4 * j4 + 2]) * inv_n;
+                        r.w = __uint_as_float(d[4 * j4 + 3]) * inv_n;
+                        if (o == 0) {
+                            const float4 bb = *reinterpret_cast<const float4*>(nxb1s + 16 * c + 4 * j4);
+                            r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + 16 * c + 4 * j4) = r;
+                    }
+                }
+            }
+        }
+        fence_before_sync();
+    }
+    named_bar(bar_id, NT_GROUP);
+    if (cur_graph >= 0 && t < 4) atomicAdd(a.vsum + (size_t)cur_graph * a.K + t, accS[t]);
+    fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc(tbase, 512);
+}
+
 }  // namespace degnn
 
 extern "C" int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
@@ -433,6 +613,35 @@ extern "C" int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
     if (grid > sm_count()) grid = sm_count();
     node_layer_tc_kernel<<<(unsigned)grid, NT_THREADS, NT_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    DEGNN_CHECK_LAUNCH();
+    return DISTEGNN_OK;
+}
+
+extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na, const float* node_feat,
+                                  const float* node_loc, const int64_t* data_batch, const float* emb_wt,
+                                  const float* emb_b, const float* layer0_params, float* h, float* x4,
+                                  int32_t* batch32, float* P, float* Q, float* Hn, float* vsum, void* stream) {
+    using namespace degnn;
+    if (int rc = check_dims(A, C, Na)) return rc;
+    if (n_nodes == 0) return DISTEGNN_OK;
+    DEGNN_CHECK_ARG(n_nodes > 0 && n_graphs > 0, "bad size");
+    DEGNN_CHECK_ARG(F >= 1 && F <= DISTEGNN_MAX_NODE_FEAT, "node_feat_nf out of range");
+    DEGNN_CHECK_ARG(node_feat && node_loc && data_batch && emb_wt && emb_b && layer0_params && h && x4 && batch32 &&
+                        P && Q && Hn && vsum, "null pointer");
+    Layout L = make_layout(A, C, Na);
+    EmbedTcArgs a;
+    a.N = n_nodes; a.B = n_graphs; a.F = F; a.K = 4 + 3 * C + H * C;
+    a.feat = node_feat; a.loc = node_loc; a.batch64 = data_batch; a.wt = emb_wt; a.bias = emb_b;
+    a.nw1a = layer0_params + L.off[DISTEGNN_P_E_W1A];
+    a.nxb1 = layer0_params + L.off[DISTEGNN_P_E_B1];
+    a.nw1b = layer0_params + L.off[DISTEGNN_P_E_W1B];
+    a.nw1h = layer0_params + L.off[DISTEGNN_P_V_W1H];
+    a.h = h; a.x4 = x4; a.batch32 = batch32; a.P = P; a.Q = Q; a.Hn = Hn; a.vsum = vsum;
+    cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM_BYTES);
+    const int64_t tiles = (n_nodes + TILE_M - 1) / TILE_M;
+    int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
+    if (grid > sm_count()) grid = sm_count();
+    embed_tc_kernel<<<(unsigned)grid, NT_THREADS, ET_SMEM_BYTES, (cudaStream_t)stream>>>(a);
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;
 }

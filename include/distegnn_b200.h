@@ -146,6 +146,13 @@ DISTEGNN_API int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A,
                        float *h, float *x4, int32_t *batch32, float *P, float *Q, float *Hn,
                        float *vsum, void *stream);
 
+/* fp32-FMA twin of distegnn_embed_fwd (cross-check only). */
+DISTEGNN_API int distegnn_embed_fwd_simt(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
+                                         const float *node_feat, const float *node_loc, const int64_t *data_batch,
+                                         const float *emb_wt, const float *emb_b, const float *layer0_params,
+                                         float *h, float *x4, int32_t *batch32, float *P, float *Q, float *Hn,
+                                         float *vsum, void *stream);
+
 /* ---- real↔real edge stage ------------------------------------------------------------------------
  * coord2radial + edge_model + the edge part of coord_model_vel + the edge part of node_model
  * (FastEGNN.py:237-246, 144-150, 169-177, 206): for every CSR edge (i=row, j=col)

@@ -195,6 +195,32 @@ def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
                 assert err <= 2e-5, (impl, name, err)
 
 
+@pytest.mark.parametrize("F,B", [(3, 1), (1, 11), (16, 2)])
+def test_embed_kernel_tensor_core_vs_fma_twin(F, B):
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    N, C = 50_003, 3
+    d = dev()
+    g = torch.Generator().manual_seed(F)
+    sd = orc.init_state_dict(F, 0, 2, 64, C, 1, seed=1)
+    m = cuda_model(dict(node_feat_nf=F, node_attr_nf=0, edge_attr_nf=2, virtual_channels=C, n_layers=1), sd)
+    pk = m._packed_params(d)
+    feat, loc = (torch.randn(N, F, generator=g) * 3).to(d), torch.randn(N, 3, generator=g).to(d)
+    batch = torch.sort(torch.randint(0, B, (N,), generator=g))[0].to(d)
+    K = 4 + 3 * C + 64 * C
+    outs = []
+    for fn in (be.embed_simt, be.embed):
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=d, dtype=dt)
+        h, x4, b32, P, Q, Hn, vsum = z(N, 64), z(N, 4), z(N, dt=torch.int32), z(N, 64), z(N, 64), z(N, 64), z(B, K)
+        fn((N, B, F, 2, C, 0), feat, loc, batch, pk["emb_wt"], pk["emb_b"], pk["layers"][0], h, x4, b32, P, Q, Hn, vsum)
+        torch.cuda.synchronize()
+        outs.append(dict(h=h, x4=x4, b32=b32.float(), P=P, Q=Q, Hn=Hn, vsum=vsum[:, :4]))
+    for k in outs[0]:
+        err = max_abs(outs[1][k], outs[0][k]) / max(1e-9, float(outs[0][k].abs().max()))
+        print(f"embed F={F} B={B} {k}: rel err {err:.3e}")
+        assert err <= 2e-5, (k, err)
+
+
 @pytest.mark.parametrize("Na,B,big", [(2, 1, False), (0, 9, False), (2, 1, True)])
 def test_node_kernel_tensor_core_vs_fma_twin(Na, B, big):
     """tcgen05 node-update kernel against its fp32-FMA twin: single graph / batch with straddling tiles, with and
