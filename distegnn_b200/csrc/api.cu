@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 
 namespace degnn {
@@ -90,6 +94,17 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+void ensure_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, kernel})) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done.insert({dev, kernel});
 }
 
 }  // namespace degnn

@@ -43,6 +43,9 @@ int check_dims(int A, int C, int Na);
     } while (0)
 
 int sm_count();   // cached multiprocessor count of the current device
+// Opt `kernel` in to `bytes` of dynamic shared memory, once per (device, kernel).  Not a stream operation, so it is
+// done on the first (eager) call and never again — nothing but launches happens under CUDA-graph capture.
+void ensure_dynamic_smem(const void* kernel, int bytes);
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float silu(float x) {

@@ -212,8 +212,7 @@ extern "C" int distegnn_edge_layer_fwd_simt(int64_t n_nodes, int64_t n_edges, in
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(edge_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)EDGE_SMEM_BYTES);
+        ensure_dynamic_smem((const void*)edge_layer_kernel, (int)EDGE_SMEM_BYTES);
         attr_set = true;
     }
     int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;

@@ -406,7 +406,7 @@ extern "C" int distegnn_edge_layer_fwd_tf32(int64_t n_nodes, int64_t n_edges, in
     int64_t grid = (tiles + 1) / 2;
     if (grid > sm_count()) grid = sm_count();
     auto launch = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        ensure_dynamic_smem((const void*)kern, (int)TC_SMEM_BYTES);
         kern<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(a);
     };
     switch (A) {

@@ -500,7 +500,7 @@ extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, 
     int64_t grid = (tiles + T16_GROUPS - 1) / T16_GROUPS;
     if (grid > sm_count()) grid = sm_count();
     auto launch = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES);
+        ensure_dynamic_smem((const void*)kern, (int)T16_SMEM_BYTES);
         kern<<<(unsigned)grid, T16_THREADS, T16_SMEM_BYTES, (cudaStream_t)stream>>>(a);
     };
     switch (A) {

@@ -608,7 +608,7 @@ extern "C" int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int
     a.nw1b = nx + L.off[DISTEGNN_P_E_W1B];
     a.nw1h = nx + L.off[DISTEGNN_P_V_W1H];
     a.h_out = h_out; a.x4_out = x4_out; a.P = P; a.Q = Q; a.Hn = Hn; a.loc_out = node_loc_out; a.vsum = vsum;
-    cudaFuncSetAttribute(node_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)node_layer_tc_kernel, (int)NT_SMEM_BYTES);
     const int64_t tiles = (n_nodes + TILE_M - 1) / TILE_M;
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
     if (grid > sm_count()) grid = sm_count();
@@ -637,7 +637,7 @@ extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, i
     a.nw1b = layer0_params + L.off[DISTEGNN_P_E_W1B];
     a.nw1h = layer0_params + L.off[DISTEGNN_P_V_W1H];
     a.h = h; a.x4 = x4; a.batch32 = batch32; a.P = P; a.Q = Q; a.Hn = Hn; a.vsum = vsum;
-    cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)embed_tc_kernel, (int)ET_SMEM_BYTES);
     const int64_t tiles = (n_nodes + TILE_M - 1) / TILE_M;
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
     if (grid > sm_count()) grid = sm_count();

@@ -234,8 +234,7 @@ extern "C" int distegnn_virtual_layer_fwd_simt(int64_t n_nodes, int n_graphs, in
     a.w3x = layer_params + L.off[DISTEGNN_P_V_W3X];
     a.agg_v = agg_v; a.trans_v = trans_v; a.vsum = vsum;
 
-    cudaFuncSetAttribute(virtual_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)VIRT_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)virtual_layer_kernel, (int)VIRT_SMEM_BYTES);
     const int TN = TILE_M / C;
     int64_t tiles = (n_nodes + TN - 1) / TN;
     int64_t grid = (int64_t)sm_count() * 2;

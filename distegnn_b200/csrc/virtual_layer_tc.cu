@@ -367,7 +367,7 @@ extern "C" int distegnn_virtual_layer_fwd_tf32(int64_t n_nodes, int n_graphs, in
     a.bx = layer_params + L.off[DISTEGNN_P_V_BX];
     a.w3x = layer_params + L.off[DISTEGNN_P_V_W3X];
     a.agg_v = agg_v; a.trans_v = trans_v; a.vsum = vsum;
-    cudaFuncSetAttribute(virtual_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)virtual_layer_tc_kernel, (int)VT_SMEM_BYTES);
     const int TN = TILE_M / C;
     const int64_t tiles = (n_nodes + TN - 1) / TN;
     int64_t grid = (tiles + 1) / 2;

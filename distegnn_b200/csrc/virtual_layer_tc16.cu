@@ -338,7 +338,7 @@ extern "C" int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, 
     a.bx = layer_params + L.off[DISTEGNN_P_V_BX];
     a.w3x = layer_params + L.off[DISTEGNN_P_V_W3X];
     a.agg_v = agg_v; a.trans_v = trans_v; a.vsum = vsum;
-    cudaFuncSetAttribute(virtual_layer_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V16_SMEM_BYTES);
+    ensure_dynamic_smem((const void*)virtual_layer_t16_kernel, (int)V16_SMEM_BYTES);
     const int TN = TILE_M / C;
     const int64_t tiles = (n_nodes + TN - 1) / TN;
     int64_t grid = (tiles + V16_GROUPS - 1) / V16_GROUPS;

@@ -184,6 +184,9 @@ class FastEGNN(nn.Module):
         self._packed = None                # (key, tensors)
         self._timing = None                # bench.py: list collecting (name, start_evt, end_evt)
         self._warned_grad = False
+        self.cuda_graph = False            # opt-in: replay the forward as a CUDA graph (see _forward_graphed)
+        self._graph_cache: Dict[tuple, tuple] = {}
+        self._graph_max_captures = 8
         self.process_group = None          # torch.distributed group for the virtual-node sync (None = WORLD)
 
     # ---- runtime helpers -----------------------------------------------------------------------
@@ -252,58 +255,104 @@ class FastEGNN(nn.Module):
         if loc_mean.shape != (B, 3):
             raise ValueError("loc_mean must be [B,3]")
         K = 4 + 3 * Cn + H * Cn
-        f32 = lambda t: t.detach().to(dtype=torch.float32).contiguous()
+        f32 = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) \
+            else t.detach().to(dtype=torch.float32).contiguous()
 
         with torch.no_grad():
             pk = self._packed_params(dev)
-            layers: List[Tensor] = pk["layers"]
             rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
             ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
-            node_feat, node_loc, node_vel = f32(node_feat), f32(node_loc), f32(node_vel)
-            attr = f32(node_attr) if Na > 0 else None
-            data_batch = data_batch.contiguous()
-
-            new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
-            h, P, Q, Hn = new(N, H), new(N, H), new(N, H), new(N, H)
-            agg_m, agg_v = new(N, H), new(N, H)
-            x4, agg_x, trans_v = new(N, 4), new(N, 4), new(N, 4)
-            batch32 = new(N, dt=torch.int32)
-            vsum = torch.zeros(B, K, dtype=torch.float32, device=dev)
-            G = new(B, Cn, H)
-            Xv = f32(loc_mean).unsqueeze(-1).repeat(1, 1, Cn).contiguous()          # FastEGNN.py:300
-            Hv = pk["hv0"].unsqueeze(0).repeat(B, 1, 1).contiguous()                # FastEGNN.py:299 (as [B,C,64])
-            out = new(N, 3)
-            base = _lib.FLAG_NORMALIZE if self.normalize else 0
-            L = self.n_layers
-
-            be.embed((N, B, F, A, Cn, Na), node_feat, node_loc, data_batch, pk["emb_wt"], pk["emb_b"],
-                     layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
-            if L == 0:
-                return node_loc.clone(), Xv
-            self._sync_virtual(vsum)
-            be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
-            for i in range(L):
-                last = i == L - 1
-                flags = base | (_lib.FLAG_LAST if last else 0)
-                lp, lp_next = layers[i], (None if last else layers[i + 1])
-                agg_x.zero_()
-                vsum.zero_()
-                if not last:
-                    agg_m.zero_()
-                t0 = self._mark("edge")
-                be.edge_layer((N, E, A, Cn, Na), flags, row, col, ea, x4, P, Q, lp,
-                              None if last else agg_m, agg_x)
-                t1 = self._mark("edge_end")
-                be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp,
-                                 None if last else agg_v, trans_v, vsum)
-                t2 = self._mark("virtual_end")
-                be.node_layer((N, B, A, Cn, Na), flags, rowptr, batch32, h, x4, node_vel, attr,
-                              None if last else agg_m, agg_x, None if last else agg_v, trans_v, lp, lp_next,
-                              None if last else h, x4, None if last else P, None if last else Q,
-                              None if last else Hn, out if last else None, vsum)
-                t3 = self._mark("node_end")
-                if self._timing is not None:
-                    self._timing.append((i, t0[1], t1[1], t2[1], t3[1]))
-                self._sync_virtual(vsum)
-                be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vsum, Xv, Hv, lp, lp_next, G)
+            args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
+                        loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
+                        data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
+            dims = (N, E, B, K)
+            if self.cuda_graph and self.world_size == 1 and self._backend is None and dev.type == "cuda" \
+                    and self._timing is None:
+                return self._forward_graphed(be, pk, dims, args)
+            ws = self._alloc_workspace(dev, N, B, K)
+            out, Xv = self._run(be, pk, dims, args, ws)
         return out, Xv
+
+    # ---- device work ---------------------------------------------------------------------------
+    def _alloc_workspace(self, dev, N: int, B: int, K: int) -> Dict[str, Tensor]:
+        Cn = self.virtual_channels
+        new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        return dict(h=new(N, H), P=new(N, H), Q=new(N, H), Hn=new(N, H), agg_m=new(N, H), agg_v=new(N, H),
+                    x4=new(N, 4), agg_x=new(N, 4), trans_v=new(N, 4), batch32=new(N, dt=torch.int32),
+                    vsum=new(B, K), G=new(B, Cn, H), Xv=new(B, 3, Cn), Hv=new(B, Cn, H), out=new(N, 3))
+
+    def _run(self, be, pk, dims, a: Dict[str, Tensor], ws: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
+        """Enqueue one forward on the current stream (buffers in `ws`; nothing allocates, nothing syncs)."""
+        A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
+        N, E, B, K = dims
+        layers: List[Tensor] = pk["layers"]
+        h, P, Q, Hn, agg_m, agg_v = ws["h"], ws["P"], ws["Q"], ws["Hn"], ws["agg_m"], ws["agg_v"]
+        x4, agg_x, trans_v, batch32 = ws["x4"], ws["agg_x"], ws["trans_v"], ws["batch32"]
+        vsum, G, Xv, Hv, out = ws["vsum"], ws["G"], ws["Xv"], ws["Hv"], ws["out"]
+        Xv.copy_(a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn))                     # FastEGNN.py:300
+        Hv.copy_(pk["hv0"].unsqueeze(0).expand(B, Cn, H))                          # FastEGNN.py:299 (as [B,C,64])
+        vsum.zero_()
+        base = _lib.FLAG_NORMALIZE if self.normalize else 0
+        L = self.n_layers
+        be.embed((N, B, F, A, Cn, Na), a["node_feat"], a["node_loc"], a["data_batch"], pk["emb_wt"], pk["emb_b"],
+                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
+        if L == 0:
+            out.copy_(a["node_loc"])
+            return out, Xv
+        self._sync_virtual(vsum)
+        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
+        for i in range(L):
+            last = i == L - 1
+            flags = base | (_lib.FLAG_LAST if last else 0)
+            lp, lp_next = layers[i], (None if last else layers[i + 1])
+            agg_x.zero_()
+            vsum.zero_()
+            if not last:
+                agg_m.zero_()
+            t0 = self._mark("edge")
+            be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp,
+                          None if last else agg_m, agg_x)
+            t1 = self._mark("edge_end")
+            be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp,
+                             None if last else agg_v, trans_v, vsum)
+            t2 = self._mark("virtual_end")
+            be.node_layer((N, B, A, Cn, Na), flags, a["rowptr"], batch32, h, x4, a["node_vel"], a["attr"],
+                          None if last else agg_m, agg_x, None if last else agg_v, trans_v, lp, lp_next,
+                          None if last else h, x4, None if last else P, None if last else Q,
+                          None if last else Hn, out if last else None, vsum)
+            t3 = self._mark("node_end")
+            if self._timing is not None:
+                self._timing.append((i, t0[1], t1[1], t2[1], t3[1]))
+            self._sync_virtual(vsum)
+            be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vsum, Xv, Hv, lp, lp_next, G)
+        return out, Xv
+
+    def _forward_graphed(self, be, pk, dims, a: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
+        """CUDA-graph replay of `_run` (opt-in: `model.cuda_graph = True`; single-partition only — capturing the
+        NCCL all-reduce of the multi-partition path is not supported in this release).  The graph is keyed by the addresses and
+        shapes of every tensor it reads, so it is valid for as long as the caller keeps passing the same (possibly
+        in-place updated) tensors — inference loops, rollouts, benchmarks.  New tensors trigger a re-capture; after
+        `_graph_max_captures` distinct keys the model falls back to eager launches for unseen keys."""
+        key = (dims, id(pk)) + tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in a.items() if v is not None)
+        ent = self._graph_cache.get(key)
+        if ent is None:
+            if len(self._graph_cache) >= self._graph_max_captures:
+                ws = self._alloc_workspace(a["node_loc"].device, dims[0], dims[2], dims[3])
+                return self._run(be, pk, dims, a, ws)
+            dev = a["node_loc"].device
+            ws = self._alloc_workspace(dev, dims[0], dims[2], dims[3])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):            # warm-up outside capture: lazy inits, NCCL communicator
+                self._run(be, pk, dims, a, ws)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = be.launches
+            with torch.cuda.graph(g):
+                self._run(be, pk, dims, a, ws)
+            ent = (g, ws, be.launches - n0, a, pk)   # keep the keyed tensors alive: their addresses are baked in
+            self._graph_cache[key] = ent
+        ent[0].replay()
+        be.launches += ent[2]
+        return ent[1]["out"].clone(), ent[1]["Xv"].clone()
