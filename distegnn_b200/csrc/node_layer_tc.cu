@@ -123,16 +123,24 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     int it = 0;
 
     const int64_t num_tiles = (a.N + TILE_M - 1) / TILE_M;
-    for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < num_tiles; tile += (int64_t)gridDim.x * NT_GROUPS, ++it) {
+    const int64_t tstride = (int64_t)gridDim.x * NT_GROUPS;
+    // TMA: one 256-byte row per node of tile `tl` into the padded staging buffer (no-op past the last tile)
+    auto stage_tile = [&](const float* src, int64_t tl) {
+        if (tl < num_tiles) {
+            const int64_t m0 = tl * TILE_M;
+            const int nv = (int)min((int64_t)TILE_M, a.N - m0);
+            if (t == 0) mbar_expect_tx(sbar, (uint32_t)nv * (H * 4));
+            if (t < nv) bulk_g2s(myrow, src + (size_t)(m0 + t) * H, H * 4, sbar);
+        }
+    };
+    stage_tile(a.h, (int64_t)blockIdx.x * NT_GROUPS + grp);      // first tile; later tiles are prefetched below
+    for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < num_tiles; tile += tstride, ++it) {
         int* sgp = sg + 2 * (it & 1);                // first/last graph id of the tile, double-buffered by tile parity
         const int64_t n0 = tile * TILE_M;
         const int nvalid = (int)min((int64_t)TILE_M, a.N - n0);
         const bool valid = t < nvalid;
         const size_t node = (size_t)(n0 + (valid ? t : 0));
-        auto stage_rows = [&](const float* src) {    // TMA: one 256-byte row per node into the padded staging buffer
-            if (t == 0) mbar_expect_tx(sbar, (uint32_t)nvalid * (H * 4));
-            if (valid) bulk_g2s(myrow, src + node * H, H * 4, sbar);
-        };
+        auto stage_rows = [&](const float* src) { stage_tile(src, tile); };
         auto staged = [&]() {
             mbar_wait(sbar, sph);
             sph ^= 1;
@@ -150,7 +158,6 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
             named_bar(bar_id, NT_GROUP);
         };
 
-        stage_rows(a.h);
         int g = -1;
         float invdeg = 0.f;
         if (valid) {
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
         }
         __syncwarp();
         if (!last) stage_rows(a.agg_m);              // staging buffer is free: everyone passed the barrier
+        else stage_tile(a.h, tile + tstride);        // last layer: h of the next tile right away
 
         // ---- while MMA 1 runs: per-node coordinate terms --------------------------------------------------
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f), ax = x, tv = x;
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
             }
             __syncwarp();
             if (next_src) stage_rows(next_src);
+            else stage_tile(a.h, tile + tstride);    // staging buffer is idle for the rest of this tile: prefetch h
             mma_done();
         };
         l1_chunk(invdeg, desc(N1hi + NT_W, NT_LBO64), desc(N1lo + NT_W, NT_LBO64), a.agg_v);

@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""torchrun entry point with the reference's CLI (reference main.py:95-163) for the accelerated hot path.
+
+    python main.py --config_path config.yaml [--model_name FastEGNN --batch_size 1 --split_mode random
+                                              --virtual_channels 8 --checkpoint best_model.pth --seed 0]
+    torchrun --nproc_per_node=P --master_addr=127.0.0.1 --master_port=29500 main.py --config_path ...
+
+It reads the reference's YAML layout (sections `model`, `data`, `seed`; e.g. config/largefluid_distegnn.yaml),
+takes the same command-line overrides, initialises `torch.distributed` exactly as the reference does
+(`init_process_group("nccl")`, rank = LOCAL_RANK, one process per GPU, main.py:143-163), builds
+`distegnn_b200.FastEGNN` through the same `get_model` switch (main.py:58-62), wraps it in
+`DistributedDataParallel(..., find_unused_parameters=True)` (main.py:196), optionally loads a reference checkpoint
+(`{'model_state_dict': ...}` with or without DDP's `module.` prefix, main.py:208-220, train.py:235-259) and runs the
+DistEGNN forward over graph partitions.
+
+What it does NOT do: the reference's datasets are not redistributable and its data pipeline needs PyG/h5py/
+MDAnalysis, so inputs are the seeded synthetic restatement of the configured dataset (`distegnn_b200/synth.py`:
+same node/edge statistics, `radius`/`split_mode` semantics of datasets/distribute_graphs.py); and this release is
+forward-only, so instead of the training loop (utils/train.py) it evaluates `--eval_steps` forward passes and
+reports graph-steps/s, edges/s and the MSE against a zero-displacement target.  Training = scope row f-1.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+
+import torch
+import torch.distributed as dist
+import yaml
+from torch.nn.parallel import DistributedDataParallel
+
+from distegnn_b200 import FastEGNN, synth
+
+
+class Cfg(dict):
+    """Attribute access over nested dicts (stand-in for easydict.EasyDict, which the reference uses)."""
+
+    def __getattr__(self, k):
+        v = self[k]
+        return Cfg(v) if isinstance(v, dict) else v
+
+    __setattr__ = dict.__setitem__
+
+
+DATASET_TO_WORKLOAD = {"nbody": "nbody100", "water3d": "water3d_10k", "water-3d": "water3d_10k",
+                       "fluid113k": "fluid113k", "largefluid": "fluid113k", "synth1m": "synth1m"}
+
+
+def get_model(cfg: Cfg, world_size: int) -> torch.nn.Module:
+    """reference main.py:58-92 — only the DistEGNN family lives here."""
+    m = cfg["model"]
+    if m["model_name"] != "FastEGNN":
+        raise NotImplementedError(f"model_name={m['model_name']!r}: only FastEGNN (DistEGNN) is accelerated here")
+    return FastEGNN(node_feat_nf=m["node_feat_nf"], node_attr_nf=m["node_attr_nf"], edge_attr_nf=m["edge_attr_nf"],
+                    hidden_nf=m["hidden_nf"], virtual_channels=m["virtual_channels"], world_size=world_size,
+                    n_layers=m["n_layers"], normalize=m["normalize"])
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--config_path", type=str, required=True, help="path to config yaml file")
+    p.add_argument("--wandb", action="store_true")
+    p.add_argument("--lr", type=float, default=None)
+    p.add_argument("--seed", type=int, default=None)
+    p.add_argument("--model_name", type=str, default=None)
+    p.add_argument("--batch_size", type=int, default=None)
+    p.add_argument("--split_mode", type=str, default=None)
+    p.add_argument("--early_stop", type=int, default=None)
+    p.add_argument("--checkpoint", type=str, default=None)
+    p.add_argument("--cutoff_rate", type=float, default=None)
+    p.add_argument("--outer_radius", type=float, default=None)
+    p.add_argument("--inner_radius", type=float, default=None)
+    p.add_argument("--virtual_channels", type=int, default=None)
+    p.add_argument("--eval_steps", type=int, default=10, help="(new) forward passes to time")
+    p.add_argument("--nodes", type=int, default=None, help="(new) override the synthetic node count")
+    return p.parse_args()
+
+
+def main():
+    args = parse()
+    with open(args.config_path) as f:
+        cfg = yaml.safe_load(f)
+    cfg.setdefault("data", {})
+    if args.seed is not None:
+        cfg["seed"] = args.seed
+    if args.model_name is not None:
+        cfg["model"]["model_name"] = args.model_name
+    if args.batch_size is not None:
+        cfg["data"]["batch_size"] = args.batch_size
+    if args.split_mode is not None:
+        cfg["data"]["split_mode"] = args.split_mode
+    if args.checkpoint is not None:
+        cfg["model"]["checkpoint"] = args.checkpoint
+    if args.inner_radius is not None:
+        cfg["data"]["inner_radius"] = args.inner_radius
+    if args.virtual_channels is not None:
+        cfg["model"]["virtual_channels"] = args.virtual_channels
+
+    assert torch.cuda.is_available(), "distegnn_b200 needs CUDA devices (there is no CPU path)"
+    distributed = "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ["WORLD_SIZE"]) if distributed else 1
+    torch.cuda.set_device(local_rank)
+    if distributed:                                            # reference main.py:159-163
+        dist.init_process_group("nccl", rank=local_rank, world_size=world_size)
+    if local_rank == 0:
+        print(f"Use {world_size} GPUs!")
+    torch.manual_seed(cfg.get("seed", 0))
+
+    model = get_model(cfg, world_size).to(local_rank)
+    ck = cfg["model"].get("checkpoint")
+    if ck:
+        state = torch.load(ck, map_location=f"cuda:{local_rank}")
+        sd = state.get("model_state_dict", state)
+        sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
+        model.load_state_dict(sd)
+    if distributed:                                            # reference main.py:194-196
+        model = DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=True)
+    model.eval()
+
+    # ---- inputs: synthetic restatement of the configured dataset, partitioned like datasets/distribute_graphs.py ----
+    d = cfg["data"]
+    name = DATASET_TO_WORKLOAD.get(str(d.get("dataset_name", "fluid113k")).lower(), "fluid113k")
+    base = synth.WORKLOADS[name]
+    m = cfg["model"]
+    w = synth.Workload(base.name, args.nodes or base.n_nodes, d.get("inner_radius", d.get("radius", base.radius)),
+                       base.degree, m["node_feat_nf"], m["node_attr_nf"], m["edge_attr_nf"], m["virtual_channels"],
+                       m["normalize"])
+    split = d.get("split_mode", "random")
+    if world_size > 1 and split not in ("random", "kmeans"):
+        if local_rank == 0:
+            print(f"split_mode={split!r} needs METIS/spectral partitioners of the reference's data pipeline; "
+                  "using 'random' for the synthetic graph")
+        split = "random"
+    part = synth.make_partitions(w, world_size=world_size, split_mode=split, seed=cfg.get("seed", 0),
+                                 only_rank=local_rank)[local_rank]
+    inp = {k: (v.to(local_rank) if v is not None else None) for k, v in part.items()}
+    n_r, e_r = inp["node_loc"].shape[0], inp["edge_index"].shape[1]
+
+    def forward():                                             # positional call as in utils/train.py:63-71
+        node_attr = inp["node_attr"] if m["node_attr_nf"] > 0 else None
+        return model(inp["node_feat"], inp["node_loc"], inp["node_vel"], inp["loc_mean"], inp["edge_index"],
+                     inp["data_batch"], inp["edge_attr"], node_attr)
+
+    with torch.no_grad():
+        for _ in range(3):
+            out, X = forward()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.eval_steps):
+            out, X = forward()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        dt = (time.perf_counter() - t0) / args.eval_steps
+        # node-count weighted MSE across ranks, as utils/train.py:98-110 weights the loss
+        se = ((out - inp["node_loc"]) ** 2).sum()
+        cnt = torch.tensor([float(n_r), float(e_r)], device=local_rank)
+        if distributed:
+            dist.all_reduce(se)
+            dist.all_reduce(cnt)
+    if local_rank == 0:
+        print(f"[{w.name}] world_size={world_size} split={split if world_size > 1 else 'none'} nodes={int(cnt[0])} "
+              f"edges(sum over partitions)={int(cnt[1])}  forward {dt * 1e3:.3f} ms  "
+              f"{1.0 / dt:.2f} graph-steps/s  {cnt[1].item() / dt / 1e6:.1f} M edges/s  "
+              f"mean squared displacement {se.item() / (3 * cnt[0].item()):.4e}  virtual_loc {tuple(X.shape)}")
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -529,3 +529,36 @@ def test_large_graph_properties():
     assert max_abs(out @ R + t, out_r) <= 1e-4
     ref, refX = orc.forward(sd, **inp)
     check_close(out, X, ref, refX, inp["node_loc"], "synth 200k")
+
+
+def test_full_size_config5_properties():
+    """BASELINE.json config 5 at FULL size on one GPU (1,000,000 nodes, ~20.6 M directed edges, C = 8): the CPU
+    oracle cannot check this size in reasonable time, so the checks are size-independent properties —
+    SE(3) equivariance (the reference's own test, atol 1e-4), invariance to the order of the edge list, run-to-run
+    reproducibility, and finiteness."""
+    w = synth.WORKLOADS["synth1m"]
+    inp = synth.make_partitions(w, seed=0)[0]
+    assert inp["node_loc"].shape[0] == 1_000_000 and inp["edge_index"].shape[1] > 20_000_000
+    sd = orc.init_state_dict(3, 2, 2, 64, 8, 4, seed=2, coord_gain=0.05)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=2, edge_attr_nf=2, virtual_channels=8, n_layers=4), sd)
+    di = to_dev(inp)
+    with torch.no_grad():
+        out, X = m(**di)
+        out2, X2 = m(**di)
+        perm = torch.randperm(inp["edge_index"].shape[1], generator=torch.Generator().manual_seed(1)).to(dev())
+        out_p, X_p = m(**{**di, "edge_index": di["edge_index"][:, perm].contiguous(),
+                          "edge_attr": di["edge_attr"][perm].contiguous()})
+        R, t = _rotation(7).to(dev()), torch.tensor([-0.7, 0.4, 1.5], device=dev())
+        out_r, X_r = m(**{**di, "node_loc": di["node_loc"] @ R + t, "node_vel": di["node_vel"] @ R,
+                          "loc_mean": di["loc_mean"] @ R + t})
+    assert torch.isfinite(out).all() and torch.isfinite(X).all()
+    disp = float((out - di["node_loc"]).abs().max())
+    assert disp > 1e-4                                               # the model really moves the particles
+    scale = max(1.0, float(out.abs().max()))
+    print(f"1M nodes: displacement scale {disp:.3e}; rerun diff {max_abs(out, out2):.2e}; "
+          f"edge-permutation diff {max_abs(out, out_p):.2e}; equivariance residual "
+          f"{max_abs(out @ R + t, out_r):.2e}; virtual {max_abs(X.permute(0, 2, 1) @ R + t, X_r.permute(0, 2, 1)):.2e}")
+    assert max_abs(out, out2) <= 2e-6 * scale and max_abs(X, X2) <= 2e-6 * scale
+    assert max_abs(out, out_p) <= 2e-6 * scale and max_abs(X, X_p) <= 2e-6 * scale
+    assert max_abs(out @ R + t, out_r) <= 1e-4
+    assert max_abs(X.permute(0, 2, 1) @ R + t, X_r.permute(0, 2, 1)) <= 1e-4
