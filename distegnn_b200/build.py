@@ -33,9 +33,9 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
-    extra = os.environ.get("DISTEGNN_NVCC_DEFS", "").split()      # e.g. "-DT16_CHUNK_UNROLL=4" for A/B builds
+def _compile(src, verbose, objdir=None, defs=None):
+    obj = os.path.join(objdir or OBJ, src[:-3] + ".o")
+    extra = os.environ.get("DISTEGNN_NVCC_DEFS", "").split() + list(defs or [])   # e.g. "-DT16_CHUNK_UNROLL=4"
     cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
@@ -65,9 +65,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defs, verbose: bool = False) -> str:
+    """A/B build: the same sources with extra -D flags -> distegnn_b200/variants/libdistegnn_b200.<tag>.so
+    (select it at run time with DISTEGNN_B200_LIB=<path>; the variants travel to the GPU box like the main .so)."""
+    vdir = os.path.join(PKG, "variants")
+    objdir = os.path.join(vdir, "build_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    srcs = sources()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose, objdir, defs), srcs))
+    lib = os.path.join(vdir, f"libdistegnn_b200.{tag}.so")
+    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "shared",
+                        "-Xlinker", "-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", metavar="TAG", help="build an A/B variant; flags via --defs")
+    ap.add_argument("--defs", default="", help="extra nvcc flags for --variant, e.g. --defs=-DDEGNN_SILU_MODE=0")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    if a.variant:
+        print(build_variant(a.variant, a.defs.split(), a.verbose))
+    else:
+        print(build(a.force, a.verbose))

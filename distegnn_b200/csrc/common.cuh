@@ -62,6 +62,108 @@ __device__ __forceinline__ float silu(float x) {
 __device__ __forceinline__ float4 silu4(float4 v) {
     return make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
 }
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 — two fp32 lanes per issue slot) --------------------
+// The tensor-core kernels are bound by instruction issue, not by the FMA pipe (ncu: issue 56 %, fma pipe 22 %), so
+// every elementwise chain around the MMAs runs on register PAIRS.  DEGNN_SILU_MODE selects the SiLU flavour:
+//   0  scalar ops (one fp32 per instruction; kept for A/B builds)
+//   1  packed: per pair FMUL2, 2 EX2, FADD2, 2 RCP, FMUL2
+//   2  packed + one reciprocal per FOUR activations:  1/d_i = d_j·d_k·d_l / (d_0 d_1 d_2 d_3)  (5 MUFU per 4 instead
+//      of 8; falls back to 4 RCPs when the product leaves the fp32 range, i.e. some x < about −21)
+#ifndef DEGNN_SILU_MODE
+#define DEGNN_SILU_MODE 2
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 bc2(float x) { return pk2(x, x); }
+#if DEGNN_SILU_MODE == 0
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { float a0, a1, b0, b1; upk2(a, a0, a1); upk2(b, b0, b1); return pk2(a0 + b0, a1 + b1); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { float a0, a1, b0, b1; upk2(a, a0, a1); upk2(b, b0, b1); return pk2(a0 - b0, a1 - b1); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { float a0, a1, b0, b1; upk2(a, a0, a1); upk2(b, b0, b1); return pk2(a0 * b0, a1 * b1); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    float a0, a1, b0, b1, c0, c1; upk2(a, a0, a1); upk2(b, b0, b1); upk2(c, c0, c1);
+    return pk2(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+}
+#else
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+#endif
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// d = 1 + 2^{-x·log2 e} for a pair
+__device__ __forceinline__ f32x2 silu_den2(f32x2 x) {
+    float t0, t1;
+    upk2(mul2(x, bc2(-1.4426950408889634f)), t0, t1);
+    return add2(pk2(ex2_approx(t0), ex2_approx(t1)), bc2(1.0f));
+}
+__device__ __forceinline__ f32x2 rcp2(f32x2 d) {
+    float d0, d1;
+    upk2(d, d0, d1);
+    return pk2(rcp_approx(d0), rcp_approx(d1));
+}
+__device__ __forceinline__ f32x2 silu2(f32x2 x) {
+#if DEGNN_SILU_MODE == 0 || defined(DEGNN_DIAG_NO_SILU)
+    float x0, x1;
+    upk2(x, x0, x1);
+    return pk2(silu(x0), silu(x1));
+#else
+    return mul2(x, rcp2(silu_den2(x)));
+#endif
+}
+// Four activations (two pairs) at once.  In mode 2 the caller owns the range guard: `qmax` accumulates the largest
+// product d0·d1·d2·d3 seen; if silu_q_overflow(qmax) the results of that batch are invalid (1/q is not a normal
+// number: some x < about −21) and must be recomputed with SAFE = true, which is the per-element-reciprocal form.
+// A guard per quad would either be if-converted by ptxas into predicated MUFUs on the hot path or, as a real
+// branch, serialise the quads — so it is hoisted to once per stage, next to the fp16-range rescue.
+constexpr float SILU_Q_LIMIT = 8.0e37f;
+#if DEGNN_SILU_MODE == 2 && !defined(DEGNN_DIAG_NO_SILU)
+constexpr bool kSiluGuard = true;
+#else
+constexpr bool kSiluGuard = false;
+#endif
+__device__ __forceinline__ bool silu_q_overflow(float qmax) { return kSiluGuard && !(qmax < SILU_Q_LIMIT); }
+template <bool SAFE>
+__device__ __forceinline__ void silu4p(f32x2& a, f32x2& b, float& qmax) {
+#if DEGNN_SILU_MODE != 2 || defined(DEGNN_DIAG_NO_SILU)
+    a = silu2(a);
+    b = silu2(b);
+#else
+    if (SAFE) {
+        a = silu2(a);
+        b = silu2(b);
+        return;
+    }
+    const f32x2 da = silu_den2(a), db = silu_den2(b);        // (d0,d1), (d2,d3), every d in [1, inf]
+    const f32x2 p = mul2(da, db);                             // (d0 d2, d1 d3)
+    float p0, p1;
+    upk2(p, p0, p1);
+    const float q = p0 * p1;
+    qmax = fmaxf(qmax, q);
+    const float r = rcp_approx(q);
+    const f32x2 u = pk2(r * p1, r * p0);                      // (1/(d0 d2), 1/(d1 d3)): two scalar FMULs land in a
+                                                              // register pair directly (a packed form needs 3 MOVs)
+    a = mul2(a, mul2(u, db));                                 // x · (1/d0, 1/d1)
+    b = mul2(b, mul2(u, da));                                 // x · (1/d2, 1/d3)
+#endif
+}
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }

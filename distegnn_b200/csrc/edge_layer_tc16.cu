@@ -20,6 +20,8 @@
 // With four tiles in flight per SM one group's MMA / barrier / memory waits are covered by the others.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -55,6 +57,7 @@ constexpr int T16_SMEM_BYTES = 4 * T16_W_HALFS * 2        // W2 hi/lo, Wc hi/lo
                                + (4 * H + DISTEGNN_MAX_EDGE_ATTR * H) * 4   // b2, bc, w3, w1r, w1e
                                + T16_GROUPS * TILE_M * 4  // srow
                                + T16_GROUPS * 4 * 4       // run-start bit masks (one word per warp)
+                               + T16_GROUPS * TILE_M * 16 // next tile's row | col | edge_attr[0..1] (T16_IDX_STAGE)
                                + 128;                     // mbarriers + tmem base
 constexpr uint32_t T16_LBO = 1024, T16_SBO = 128;         // fp16 K-major no-swizzle: 8 rows x 8 halfs per core matrix
 constexpr float T16_RANGE = 3.0e4f;
@@ -62,6 +65,19 @@ constexpr float T16_RANGE = 3.0e4f;
 #define T16_CHUNK_UNROLL 2     // chunks (of 16 columns) unrolled per stage loop: trades code size (I-cache) for ILP
 #endif
 constexpr int kChunkUnroll = T16_CHUNK_UNROLL;
+// A/B knobs (python -m distegnn_b200.build --variant TAG --defs=...): the defaults are the measured winners.
+#ifndef T16_Q_COPY
+#define T16_Q_COPY 0        // neighbour rows Q[col] -> shared: 0 = one TMA bulk copy per edge (UBLKCP needs uniform
+#endif                      // operands: ptxas emits a 9-instruction loop over the 32 lanes), 1 = 16 LDGSTS per thread
+                            // (measured: 3.72 ms vs 2.89 ms for the TMA form — scattered 16-byte LDGSTS lose)
+#ifndef T16_SEGSUM
+#define T16_SEGSUM 1        // segment sum of m: 0 = thread per (column, half tile), scalar; 1 = thread per (column
+#endif                      // pair, quarter tile): LDS.64 + FADD2, one RED.v2 per run
+#ifndef T16_IDX_STAGE
+#define T16_IDX_STAGE 1     // next tile's (row, col, edge_attr): 0 = LDG into registers at mid-iteration (dependent
+#endif                      // x4 / P-prefetch addresses stall on it), 1 = LDGSTS into shared one stage earlier
+constexpr std::false_type kFast{};   // silu4p flavour tags (common.cuh)
+constexpr std::true_type kSafe{};
 
 // weight W[n][k] = wt_kmajor[k*64+n] -> fp16 hi/lo at (k/8)*512 + (n/8)*64 + (n%8)*8 + k%8 (in halfs)
 __device__ __forceinline__ void stage_weight_f16(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int tid,
@@ -89,15 +105,19 @@ __device__ __forceinline__ void issue_gemm_f16x3(uint32_t d, uint32_t a_hi, uint
     umma::mma_commit(bar);
 }
 
-// 16 fp32 values (·s) -> 8 packed hi words + 8 packed lo words; `mx` tracks the running max of the hi halves
+// 16 fp32 values held as 8 register pairs (·s) -> 8 packed hi words + 8 packed lo words; `mx` tracks the running
+// max of the hi halves.  Per pair: F2FP, 2 HADD2.F32 (unpack), FADD2, F2FP, HMNMX2.
 template <bool SCALED>
-__device__ __forceinline__ void split16(const float (&v)[16], float s, uint32_t (&hi)[8], uint32_t (&lo)[8], __half2& mx) {
+__device__ __forceinline__ void split16(const f32x2 (&v)[8], float s, uint32_t (&hi)[8], uint32_t (&lo)[8], __half2& mx) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float x0 = SCALED ? v[2 * j] * s : v[2 * j], x1 = SCALED ? v[2 * j + 1] * s : v[2 * j + 1];
+        const f32x2 x = SCALED ? mul2(v[j], bc2(s)) : v[j];
+        float x0, x1, l0, l1;
+        upk2(x, x0, x1);
         const __half2 h = __floats2half2_rn(x0, x1);            // x0 -> low half (even k)
         const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        upk2(sub2(x, pk2(hf.x, hf.y)), l0, l1);
+        const __half2 l = __floats2half2_rn(l0, l1);
         mx = __hmax2(mx, h);
         hi[j] = *reinterpret_cast<const uint32_t*>(&h);
         lo[j] = *reinterpret_cast<const uint32_t*>(&l);
@@ -131,7 +151,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
     float* w1es = w1rs + H;
     int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);   // [4][128]
     uint32_t* rmask_all = reinterpret_cast<uint32_t*>(srow_all + T16_GROUPS * TILE_M);   // [4][4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rmask_all + T16_GROUPS * 4);      // [4][2]
+    int* nidx_all = reinterpret_cast<int*>(rmask_all + T16_GROUPS * 4);               // [4][row 128 | col 128 | ea 256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nidx_all + T16_GROUPS * TILE_M * 4);  // [4][2]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * T16_GROUPS);
 
     const int tid = threadIdx.x;
@@ -152,7 +173,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         w3s[tid] = a.w3[tid];
         w1rs[tid] = a.w1r[tid];
     }
-    for (int i = tid; i < A * H; i += T16_THREADS) w1es[i] = a.w1e[i];
+    for (int i = tid; i < DISTEGNN_MAX_EDGE_ATTR * H; i += T16_THREADS) w1es[i] = i < A * H ? a.w1e[i] : 0.f;   // zero rows: the generic (AT < 0) loop runs over all AMAX
     if (tid == 0) {
         for (int i = 0; i < 2 * T16_GROUPS; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
@@ -175,6 +196,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
     float* myq = qb + t * T16_QROW;
     int* srow = srow_all + grp * TILE_M;
     uint32_t* rmask = rmask_all + grp * 4;
+    int* nrow_s = nidx_all + grp * TILE_M * 4;
+    int* ncol_s = nrow_s + TILE_M;
+    float* nea_s = reinterpret_cast<float*>(ncol_s + TILE_M);      // [128][2]
     uint64_t* qbar = bars + grp * 2;
     uint64_t* mbar = bars + grp * 2 + 1;
     const uint32_t bar_id = 1 + grp;
@@ -202,13 +226,54 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
                 if (k < A) ea[k] = __ldg(a.ea + e * A + k);
         }
     };
+    constexpr bool kIdxStage = T16_IDX_STAGE && (AT == 1 || AT == 2 || AT == 0);
     auto prefetch_q = [&](int64_t tl, int r, int c) {
+#if T16_Q_COPY == 0
         if (tl < num_tiles) {
             if (t == 0) {
                 const int64_t nvalid = min((int64_t)TILE_M, a.E - tl * TILE_M);
                 mbar_expect_tx(qbar, (uint32_t)nvalid * (H * 4));
             }
             if (r >= 0) bulk_g2s(myq, a.Q + (size_t)c * H, H * 4, qbar);
+        }
+#else
+        if (tl < num_tiles && r >= 0) {              // thread t copies (and later reads) row t: no barrier needed
+            const float* src = a.Q + (size_t)c * H;
+#pragma unroll
+            for (int k = 0; k < H / 4; ++k) cp_async16(myq + 4 * k, src + 4 * k);
+        }
+        cp_async_commit();
+#endif
+    };
+    // T16_IDX_STAGE: start the copy of tile tl's (row, col, edge_attr) of this thread's edge into shared memory
+    auto stage_idx = [&](int64_t tl) {
+        const int64_t e = tl * TILE_M + t;
+        if (tl < num_tiles && e < a.E) {
+            cp_async4(nrow_s + t, a.row + e);
+            cp_async4(ncol_s + t, a.col + e);
+            if (AT == 1) cp_async4(nea_s + 2 * t, a.ea + e);
+            if (AT == 2) cp_async8(nea_s + 2 * t, a.ea + e * 2);
+        }
+        cp_async_commit();
+    };
+    auto take_idx = [&](int64_t tl, int& r, int& rr, int& c, float (&ea)[AMAX]) {
+        const int64_t e = tl * TILE_M + t;
+        r = -1;
+        rr = 0;
+        c = 0;
+#pragma unroll
+        for (int k = 0; k < AMAX; ++k) ea[k] = 0.f;
+        cp_async_wait_all();
+        if (tl < num_tiles && e < a.E) {
+            r = nrow_s[t];
+            c = ncol_s[t];
+            rr = r;
+            if (AT == 1) ea[0] = nea_s[2 * t];
+            if (AT == 2) {
+                const float2 v = *reinterpret_cast<const float2*>(nea_s + 2 * t);
+                ea[0] = v.x;
+                ea[AMAX - 1] = v.y;
+            }
         }
     };
 
@@ -227,20 +292,36 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
 
     for (int it = 0; tile < num_tiles; ++it, tile += stride) {
         // ---- stage 1: a1 = SiLU(P_i + Q_j + w_r·r + W_e·a) -> fp16 hi/lo -> TMEM ---------------------------
+#if T16_Q_COPY == 0
         mbar_wait(qbar, (uint32_t)(it & 1));
         __syncwarp();
+#else
+        cp_async_wait_all();                   // this thread's own row of Q is in shared memory
+#endif
+        if (kIdxStage) stage_idx(tile + stride);
         const float* prow = a.P + (size_t)rr_c * H;
-        auto pre_chunk = [&](int c, float (&v)[16]) {
+        const f32x2 rad2 = bc2(radial);
+        float qmax = 0.f;                  // SiLU batch-reciprocal range guard (common.cuh silu4p)
+        auto pre_chunk = [&](int c, f32x2 (&v)[8], auto safe) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const int cc = 16 * c + 4 * j4;
-                float4 pre = fma4(radial, *reinterpret_cast<const float4*>(w1rs + cc),
-                                  add4(ldg4(prow + cc), *reinterpret_cast<const float4*>(myq + cc)));
+                const ulonglong2 pp = __ldg(reinterpret_cast<const ulonglong2*>(prow + cc));
+                const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(myq + cc);
+                const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(w1rs + cc);
+                f32x2 p0 = fma2(rad2, wr.x, add2(pp.x, qq.x)), p1 = fma2(rad2, wr.y, add2(pp.y, qq.y));
 #pragma unroll
                 for (int k = 0; k < AMAX; ++k)
-                    if (k < A) pre = fma4(ea_c[k], *reinterpret_cast<const float4*>(w1es + k * H + cc), pre);
-                pre = silu4(pre);
-                v[4 * j4 + 0] = pre.x; v[4 * j4 + 1] = pre.y; v[4 * j4 + 2] = pre.z; v[4 * j4 + 3] = pre.w;
+                    if (AT < 0 || k < A) {         // AT < 0: ea_c[k] = 0 and zero weight rows beyond A (a predicated
+                                                   // FFMA2 chain here crashes ptxas 12.9 at -O2 and above)
+                        const ulonglong2 we = *reinterpret_cast<const ulonglong2*>(w1es + k * H + cc);
+                        const f32x2 e2 = bc2(ea_c[k]);
+                        p0 = fma2(e2, we.x, p0);
+                        p1 = fma2(e2, we.y, p1);
+                    }
+                silu4p<decltype(safe)::value>(p0, p1, qmax);
+                v[2 * j4] = p0;
+                v[2 * j4 + 1] = p1;
             }
         };
         float inv_s1 = 1.0f;
@@ -248,29 +329,34 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
             __half2 mx = __floats2half2_rn(0.f, 0.f);
 #pragma unroll kChunkUnroll
             for (int c = 0; c < 4; ++c) {
-                float v[16];
+                f32x2 v[8];
                 uint32_t hi[8], lo[8];
-                pre_chunk(c, v);
+                pre_chunk(c, v, kFast);
                 split16<false>(v, 1.0f, hi, lo, mx);
                 tmem_st8(lane_off + tA_hi + 8 * c, hi);
                 tmem_st8(lane_off + tA_lo + 8 * c, lo);
             }
-            if (__any_sync(FULL, row_overflow(mx))) {      // cold: some row of this warp leaves the fp16 range
+            if (__any_sync(FULL, row_overflow(mx) || silu_q_overflow(qmax))) {   // cold: a row of this warp leaves the
+                                                                                  // fp16 range, or the SiLU batch guard fired
                 float fm = 0.f, sc;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    float v[16];
-                    pre_chunk(c, v);
+                    f32x2 v[8];
+                    pre_chunk(c, v, kSafe);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) fm = fmaxf(fm, v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        float v0, v1;
+                        upk2(v[j], v0, v1);
+                        fm = fmaxf(fm, fmaxf(v0, v1));
+                    }
                 }
                 range_scale(fm, sc, inv_s1);
                 wait_st();
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    float v[16];
+                    f32x2 v[8];
                     uint32_t hi[8], lo[8];
-                    pre_chunk(c, v);
+                    pre_chunk(c, v, kSafe);
                     split16<true>(v, sc, hi, lo, mx);
                     tmem_st8(lane_off + tA_hi + 8 * c, hi);
                     tmem_st8(lane_off + tA_lo + 8 * c, lo);
@@ -295,7 +381,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         }
         int row_n, rr_n, col_n;
         float ea_n[AMAX];
-        load_edge(tile + stride, row_n, rr_n, col_n, ea_n);
+        if (kIdxStage) take_idx(tile + stride, row_n, rr_n, col_n, ea_n);
+        else load_edge(tile + stride, row_n, rr_n, col_n, ea_n);
         prefetch_l1(a.P + (size_t)rr_n * H);
         prefetch_l1(a.P + (size_t)rr_n * H + 32);
         const float4 xi_n = ldg4(a.x4 + (size_t)rr_n * 4), xj_n = ldg4(a.x4 + (size_t)col_n * 4);
@@ -305,21 +392,22 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         fence_after_sync();
 
         // ---- stage 2: m = SiLU(D/s + b2) -> row to shared (segment sum) and fp16 hi/lo -> TMEM ---------------
-        auto m_chunk = [&](int c, float (&v)[16], bool store) {
+        qmax = 0.f;
+        auto m_chunk = [&](int c, f32x2 (&v)[8], bool store, float inv_s, auto safe) {
             uint32_t d[16];
             tmem_ld16(lane_off + tD + 16 * c, d);
             wait_ld();
+            const f32x2 is2 = bc2(inv_s);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const int cc = 16 * c + 4 * j4;
-                const float4 bb = *reinterpret_cast<const float4*>(b2s + cc);
-                float4 m;
-                m.x = silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv_s1, bb.x));
-                m.y = silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv_s1, bb.y));
-                m.z = silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv_s1, bb.z));
-                m.w = silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv_s1, bb.w));
-                if (store) *reinterpret_cast<float4*>(myq + cc) = m;
-                v[4 * j4 + 0] = m.x; v[4 * j4 + 1] = m.y; v[4 * j4 + 2] = m.z; v[4 * j4 + 3] = m.w;
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(b2s + cc);
+                f32x2 m0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
+                f32x2 m1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+                silu4p<decltype(safe)::value>(m0, m1, qmax);
+                if (store) *reinterpret_cast<ulonglong2*>(myq + cc) = make_ulonglong2(m0, m1);
+                v[2 * j4] = m0;
+                v[2 * j4 + 1] = m1;
             }
         };
         float inv_s2 = 1.0f;
@@ -327,29 +415,33 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
             __half2 mx = __floats2half2_rn(0.f, 0.f);
 #pragma unroll kChunkUnroll
             for (int c = 0; c < 4; ++c) {
-                float v[16];
+                f32x2 v[8];
                 uint32_t hi[8], lo[8];
-                m_chunk(c, v, need_m);
+                m_chunk(c, v, need_m, inv_s1, kFast);
                 split16<false>(v, 1.0f, hi, lo, mx);
                 tmem_st8(lane_off + tA_hi + 8 * c, hi);
                 tmem_st8(lane_off + tA_lo + 8 * c, lo);
             }
-            if (__any_sync(FULL, row_overflow(mx))) {      // cold
+            if (__any_sync(FULL, row_overflow(mx) || silu_q_overflow(qmax))) {      // cold
                 float fm = 0.f, sc;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    float v[16];
-                    m_chunk(c, v, false);
+                    f32x2 v[8];
+                    m_chunk(c, v, need_m, inv_s1, kSafe);      // also rewrites the m row in shared memory
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) fm = fmaxf(fm, v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        float v0, v1;
+                        upk2(v[j], v0, v1);
+                        fm = fmaxf(fm, fmaxf(v0, v1));
+                    }
                 }
                 range_scale(fm, sc, inv_s2);
                 wait_st();
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    float v[16];
+                    f32x2 v[8];
                     uint32_t hi[8], lo[8];
-                    m_chunk(c, v, false);
+                    m_chunk(c, v, false, inv_s1, kSafe);
                     split16<true>(v, sc, hi, lo, mx);
                     tmem_st8(lane_off + tA_hi + 8 * c, hi);
                     tmem_st8(lane_off + tA_lo + 8 * c, lo);
@@ -371,6 +463,32 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
 #else
         if (need_m) {
 #endif
+#if T16_SEGSUM == 1
+            // warp wq <-> edges 32wq .. 32wq+31 of the tile, lane <-> columns 2·lane, 2·lane+1: per edge one LDS.64 and
+            // one FADD2; the run structure (bit mask of run starts) is warp-uniform, one RED.v2 per run and lane
+            const float* colp = qb + (32 * wq) * T16_QROW + 2 * lane;
+            uint32_t M = rmask[wq] | 1u;
+            while (M) {
+                const int e0 = __ffs((int)M) - 1;
+                M &= M - 1;
+                const int e1 = M ? __ffs((int)M) - 1 : 32;
+                f32x2 s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull;          // (+0, +0)
+                int e = e0;
+                for (; e + 3 < e1; e += 4) {
+                    s0 = add2(s0, *reinterpret_cast<const f32x2*>(colp + e * T16_QROW));
+                    s1 = add2(s1, *reinterpret_cast<const f32x2*>(colp + (e + 1) * T16_QROW));
+                    s2 = add2(s2, *reinterpret_cast<const f32x2*>(colp + (e + 2) * T16_QROW));
+                    s3 = add2(s3, *reinterpret_cast<const f32x2*>(colp + (e + 3) * T16_QROW));
+                }
+                for (; e < e1; ++e) s0 = add2(s0, *reinterpret_cast<const f32x2*>(colp + e * T16_QROW));
+                const int r = srow[32 * wq + e0];
+                if (r >= 0) {
+                    float v0, v1;
+                    upk2(add2(add2(s0, s1), add2(s2, s3)), v0, v1);
+                    red_add_v2(a.agg_m + (size_t)r * H + 2 * lane, v0, v1);
+                }
+            }
+#else
             // thread (column c, half of the tile): one RED per (run of equal destination row, column)
             const int c = t & 63, hh = t >> 6, eb = hh * 64;
             const float* colp = qb + eb * T16_QROW + c;
@@ -407,7 +525,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
                 }
                 if (cur >= 0) atomicAdd(a.agg_m + (size_t)cur * H + c, s0);
             }
+#endif
+#if T16_Q_COPY == 0
             fence_proxy_async_smem();          // generic accesses to qb ordered before the TMA refill below
+#endif
         }
         named_bar(bar_id, T16_GROUP);          // whole group done with the staging buffer
         prefetch_q(tile + stride, row_n, col_n);
@@ -417,23 +538,35 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
         fence_after_sync();
 
         // ---- stage 3: φ = w3·SiLU(D/s + bc); Δx·φ summed per destination row --------------------------------
-        float ph0 = 0.f, ph1 = 0.f, ph2 = 0.f, ph3 = 0.f;      // four independent FMA chains
+        f32x2 ph01, ph23;                                       // four independent FMA chains in two register pairs
+        qmax = 0.f;
+        auto phi_pass = [&](auto safe) {
+            ph01 = bc2(0.f);
+            ph23 = bc2(0.f);
+            const f32x2 is2 = bc2(inv_s2);
 #pragma unroll kChunkUnroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t d[16];
-            tmem_ld16(lane_off + tD + 16 * c, d);
-            wait_ld();
+            for (int c = 0; c < 4; ++c) {
+                uint32_t d[16];
+                tmem_ld16(lane_off + tD + 16 * c, d);
+                wait_ld();
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const int cc = 16 * c + 4 * j4;
-                const float4 bb = *reinterpret_cast<const float4*>(bcs + cc);
-                const float4 ww = *reinterpret_cast<const float4*>(w3s + cc);
-                ph0 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv_s2, bb.x)), ww.x, ph0);
-                ph1 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv_s2, bb.y)), ww.y, ph1);
-                ph2 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv_s2, bb.z)), ww.z, ph2);
-                ph3 = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv_s2, bb.w)), ww.w, ph3);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cc = 16 * c + 4 * j4;
+                    const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(bcs + cc);
+                    const ulonglong2 ww = *reinterpret_cast<const ulonglong2*>(w3s + cc);
+                    f32x2 s0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
+                    f32x2 s1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+                    silu4p<decltype(safe)::value>(s0, s1, qmax);
+                    ph01 = fma2(s0, ww.x, ph01);
+                    ph23 = fma2(s1, ww.y, ph23);
+                }
             }
-        }
+        };
+        phi_pass(kFast);
+        if (kSiluGuard && __any_sync(FULL, silu_q_overflow(qmax))) phi_pass(kSafe);      // cold
+        float ph0, ph1, ph2, ph3;
+        upk2(ph01, ph0, ph1);
+        upk2(ph23, ph2, ph3);
         const float phi = (ph0 + ph1) + (ph2 + ph3);
         fence_before_sync();                   // D reads ordered before the next tile's MMA 1
         {

@@ -166,6 +166,17 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         const int64_t n0 = tile * TN;
         const int nvalid = (int)min((int64_t)TN, a.N - n0);
         const int rows = nvalid * C;
+        {   // pull the next tile's inputs (a contiguous block of Hn rows, x4, graph ids) into L1 while this one computes:
+            // stage 1 otherwise spends more than half of its time waiting for exactly these loads
+            const int64_t nn0 = (tile + (int64_t)gridDim.x * V16_GROUPS) * TN;
+            const int nnv = (int)min((int64_t)TN, a.N - nn0);
+            for (int i = t; i < 2 * nnv; i += V16_GROUP) prefetch_l1(a.Hn + (size_t)nn0 * H + 32 * i);
+            if (nnv > 0) {
+                if (t < (nnv * 16 + 127) / 128) prefetch_l1(a.x4 + (size_t)nn0 * 4 + 32 * t);
+                if (t == 127) prefetch_l1(a.batch + nn0);
+                if (t == 126) prefetch_l1(a.batch + nn0 + nnv - 1);
+            }
+        }
         if (t < TN) sgraph[t] = (t < nvalid) ? __ldg(a.batch + n0 + t) : -1;
         named_bar(bar_id, V16_GROUP);
         const int g_first = sgraph[0], g_last = sgraph[nvalid - 1];
@@ -192,14 +203,20 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         }
         const float* hrow = a.Hn + node * H;
         const float* grow = a.G + ((size_t)g * C + ch) * H;
-        const float inv1 = tc16::encode_row(
-            [&](int c, float (&v)[16], bool) {
+        const f32x2 vr2 = bc2(vr);
+        const float inv1 = tc16::encode_row2(
+            [&](int c, f32x2 (&v)[8], bool, auto safe, float& qmax) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int cc = 16 * c + 4 * j4;
-                    float4 pre = silu4(fma4(vr, *reinterpret_cast<const float4*>(w1rs + cc), add4(ldg4(hrow + cc), ldg4(grow + cc))));
-                    if (!rvalid) pre = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * j4 + 0] = pre.x; v[4 * j4 + 1] = pre.y; v[4 * j4 + 2] = pre.z; v[4 * j4 + 3] = pre.w;
+                    const ulonglong2 hh = __ldg(reinterpret_cast<const ulonglong2*>(hrow + cc));
+                    const ulonglong2 gg = __ldg(reinterpret_cast<const ulonglong2*>(grow + cc));
+                    const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(w1rs + cc);
+                    f32x2 p0 = fma2(vr2, wr.x, add2(hh.x, gg.x)), p1 = fma2(vr2, wr.y, add2(hh.y, gg.y));
+                    silu4p<decltype(safe)::value>(p0, p1, qmax);
+                    if (!rvalid) p0 = p1 = 0ull;
+                    v[2 * j4] = p0;
+                    v[2 * j4 + 1] = p1;
                 }
             },
             lane_off + tA_hi, lane_off + tA_lo);
@@ -208,22 +225,22 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         mma_done();
 
         // ---- stage 2: mv = SiLU(D + b2v) -> shared tile and A ---------------------------------------------
-        const float inv2 = tc16::encode_row(
-            [&](int c, float (&v)[16], bool first) {
+        const float inv2 = tc16::encode_row2(
+            [&](int c, f32x2 (&v)[8], bool first, auto safe, float& qmax) {
                 uint32_t d[16];
                 tmem_ld16(lane_off + tD + 16 * c, d);
                 wait_ld();
+                const f32x2 is2 = bc2(inv1);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int cc = 16 * c + 4 * j4;
-                    const float4 bb = *reinterpret_cast<const float4*>(b2s + cc);
-                    float4 m;
-                    m.x = silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv1, bb.x));
-                    m.y = silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv1, bb.y));
-                    m.z = silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv1, bb.z));
-                    m.w = silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv1, bb.w));
-                    if (first && need_feat) *reinterpret_cast<float4*>(myrow + cc) = m;
-                    v[4 * j4 + 0] = m.x; v[4 * j4 + 1] = m.y; v[4 * j4 + 2] = m.z; v[4 * j4 + 3] = m.w;
+                    const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(b2s + cc);
+                    f32x2 m0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
+                    f32x2 m1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+                    silu4p<decltype(safe)::value>(m0, m1, qmax);
+                    if (first && need_feat) *reinterpret_cast<ulonglong2*>(myrow + cc) = make_ulonglong2(m0, m1);
+                    v[2 * j4] = m0;
+                    v[2 * j4 + 1] = m1;
                 }
             },
             lane_off + tA_hi, lane_off + tA_lo);
@@ -231,32 +248,54 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         issue(dWxvhi, dWxvlo);
         // pools of mv while MMA 2 runs
         if (need_feat) {
-            const int c64 = t & 63, q2 = t >> 6;
-            const float invC = 1.0f / (float)C;
-            for (int n = q2; n < nvalid; n += 2) {          // mean over channels per node
-                float s = 0.f;
-                for (int c = 0; c < C; ++c) s += tile_s[(n * C + c) * V16_ROW + c64];
-                a.agg_v[(size_t)(n0 + n) * H + c64] = s * invC;
+            // thread <-> (column pair, quarter): one LDS.64 + one FADD2 per two elements, two chains per sum
+            const int c2 = 2 * (t & 31), q4 = t >> 5;
+            auto ld2 = [](const float* p) { return *reinterpret_cast<const f32x2*>(p); };
+            const f32x2 invC2 = bc2(1.0f / (float)C);
+            for (int n = q4; n < nvalid; n += 4) {          // mean over channels per node
+                const float* base = tile_s + (n * C) * V16_ROW + c2;
+                f32x2 s0 = 0ull, s1 = 0ull;
+                int c = 0;
+                for (; c + 1 < C; c += 2) {
+                    s0 = add2(s0, ld2(base + c * V16_ROW));
+                    s1 = add2(s1, ld2(base + (c + 1) * V16_ROW));
+                }
+                if (c < C) s0 = add2(s0, ld2(base + c * V16_ROW));
+                *reinterpret_cast<f32x2*>(a.agg_v + (size_t)(n0 + n) * H + c2) = mul2(add2(s0, s1), invC2);
             }
             if (single) {                                    // sum over nodes per channel
-                for (int c = q2; c < C; c += 2) {
-                    float s = 0.f;
-                    for (int n = 0; n < nvalid; ++n) s += tile_s[(n * C + c) * V16_ROW + c64];
-                    accH[c * H + c64] += s;
+                for (int c = q4; c < C; c += 4) {
+                    const float* base = tile_s + c * V16_ROW + c2;
+                    const int nstep = C * V16_ROW;
+                    f32x2 s0 = 0ull, s1 = 0ull;
+                    int n = 0;
+                    for (; n + 1 < nvalid; n += 2) {
+                        s0 = add2(s0, ld2(base + n * nstep));
+                        s1 = add2(s1, ld2(base + (n + 1) * nstep));
+                    }
+                    if (n < nvalid) s0 = add2(s0, ld2(base + n * nstep));
+                    f32x2* acc = reinterpret_cast<f32x2*>(accH + c * H + c2);
+                    *acc = add2(*acc, add2(s0, s1));
                 }
             } else {
-                for (int n = q2; n < nvalid; n += 2) {
-                    float* dst = a.vsum + (size_t)sgraph[n] * K + 4 + 3 * C;
-                    for (int c = 0; c < C; ++c) atomicAdd(dst + c * H + c64, tile_s[(n * C + c) * V16_ROW + c64]);
+                for (int n = q4; n < nvalid; n += 4) {
+                    float* dst = a.vsum + (size_t)sgraph[n] * K + 4 + 3 * C + c2;
+                    for (int c = 0; c < C; ++c) {
+                        float v0, v1;
+                        upk2(ld2(tile_s + (n * C + c) * V16_ROW + c2), v0, v1);
+                        atomicAdd(dst + c * H, v0);
+                        atomicAdd(dst + c * H + 1, v1);
+                    }
                 }
             }
         }
         mma_done();
 
         // ---- stage 3a: φ_xv = w3xv·SiLU(D + bxv) --------------------------------------------------------
-        auto head = [&](const float* bs, const float* ws) {
-            float phi = 0.f;
-#pragma unroll
+        auto head_pass = [&](const float* bs, const float* ws, auto safe, float& qmax) {
+            f32x2 ph01 = bc2(0.f), ph23 = bc2(0.f);
+            const f32x2 is2 = bc2(inv2);
+#pragma unroll tc16::kChunkUnroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t d[16];
                 tmem_ld16(lane_off + tD + 16 * c, d);
@@ -264,14 +303,24 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int cc = 16 * c + 4 * j4;
-                    const float4 bb = *reinterpret_cast<const float4*>(bs + cc);
-                    const float4 ww = *reinterpret_cast<const float4*>(ws + cc);
-                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 0]), inv2, bb.x)), ww.x, phi);
-                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 1]), inv2, bb.y)), ww.y, phi);
-                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 2]), inv2, bb.z)), ww.z, phi);
-                    phi = fmaf(silu(fmaf(__uint_as_float(d[4 * j4 + 3]), inv2, bb.w)), ww.w, phi);
+                    const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(bs + cc);
+                    const ulonglong2 ww = *reinterpret_cast<const ulonglong2*>(ws + cc);
+                    f32x2 s0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
+                    f32x2 s1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+                    silu4p<decltype(safe)::value>(s0, s1, qmax);
+                    ph01 = fma2(s0, ww.x, ph01);
+                    ph23 = fma2(s1, ww.y, ph23);
                 }
             }
+            float p0, p1, p2, p3;
+            upk2(ph01, p0, p1);
+            upk2(ph23, p2, p3);
+            return (p0 + p1) + (p2 + p3);
+        };
+        auto head = [&](const float* bs, const float* ws) {
+            float qmax = 0.f;
+            float phi = head_pass(bs, ws, tc16::kFast, qmax);
+            if (kSiluGuard && __any_sync(FULL, silu_q_overflow(qmax))) phi = head_pass(bs, ws, tc16::kSafe, qmax);   // cold
             return phi;
         };
         phis[t] = head(bxvs, w3xvs);

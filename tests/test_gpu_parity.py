@@ -161,6 +161,48 @@ def test_edge_kernel_fp16_range_rescue():
     assert e_f16[1] <= max(8 * e_simt[1], 2e-5) and e_f16[1] <= 1e-3
 
 
+def test_edge_kernel_silu_batch_guard():
+    """The tensor-core kernels take one reciprocal per FOUR SiLUs (1/d_i from the product d0·d1·d2·d3, common.cuh
+    silu4p).  Pre-activations around −20 … −45 make that product leave the fp32 range while every single d stays
+    finite; the stage-level guard must then redo the rows with per-element reciprocals.  Rows with such
+    pre-activations sit next to ordinary ones in the same warp / quad."""
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    w = synth.WORKLOADS["water3d_10k"]
+    inp = to_dev(synth.make_partitions(w, n_nodes=20_000, seed=11)[0])
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 1, seed=3, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=1), sd)
+    lp = m._packed_params(dev())["layers"][0]
+    N, E = inp["node_loc"].shape[0], inp["edge_index"].shape[1]
+    rowptr, row, col, perm = be.build_csr(inp["edge_index"], N)
+    ea = be.gather_rows(inp["edge_attr"], perm)
+    g = torch.Generator().manual_seed(5)
+    P, Q = torch.randn(N, 64, generator=g), torch.randn(N, 64, generator=g)
+    shifted = torch.rand(N, generator=g) < 0.1                    # 10 % of the destination rows
+    shift = torch.where(shifted, -(18 + 30 * torch.rand(N, generator=g)), torch.zeros(N))
+    cols = torch.rand(N, 64, generator=g) < 0.3                   # only some columns: mixed quads
+    P = (P + shift[:, None] * cols).to(dev())
+    Q = Q.to(dev())
+    x4 = torch.zeros(N, 4, device=dev())
+    x4[:, :3] = inp["node_loc"]
+    outs = []
+    for fn in (be.edge_layer_simt, be.edge_layer):
+        agg_m, agg_x = torch.zeros(N, 64, device=dev()), torch.zeros(N, 4, device=dev())
+        fn((N, E, 2, 3, 0), 0, row, col, ea, x4, P, Q, lp, agg_m, agg_x)
+        torch.cuda.synchronize()
+        outs.append((agg_m, agg_x[:, :3]))
+    ref_m, ref_x = torch.zeros(N, 64, device=dev(), dtype=torch.float64), torch.zeros(N, 4, device=dev(),
+                                                                                      dtype=torch.float64)
+    ShadowBackend().edge_layer((N, E, 2, 3, 0), 0, row, col, ea.double(), x4.double(), P.double(), Q.double(),
+                               lp.double(), ref_m, ref_x)
+    assert torch.isfinite(outs[1][0]).all() and torch.isfinite(outs[1][1]).all()
+    e_m = float((outs[1][0].double() - ref_m).abs().max() / ref_m.abs().max())
+    e_x = float((outs[1][1].double() - ref_x[:, :3]).abs().max() / ref_x[:, :3].abs().max())
+    e_m0 = float((outs[0][0].double() - ref_m).abs().max() / ref_m.abs().max())
+    print(f"silu batch guard: rel err vs fp64  agg_m {e_m:.2e} (fp32-FMA twin {e_m0:.2e})  agg_x {e_x:.2e}")
+    assert e_m <= 5e-6 and e_x <= 5e-5
+
+
 @pytest.mark.parametrize("C,B", [(8, 1), (5, 1), (3, 7)])
 def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
     """tcgen05 virtual-stage kernel against its fp32-FMA twin (single graph and a batch whose tiles
