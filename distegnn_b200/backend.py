@@ -83,6 +83,13 @@ class CudaBackend:
                                                self._s(x4)), "edge_layer_fwd")
         self.launches += 1 if E else 0
 
+    def edge_layer_t16(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
+        """thread-per-row tcgen05 twin of edge_layer (cross-check / A-B timing only)."""
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_fwd_t16(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
+                                                   ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
+                                                   ptr(agg_x), self._s(x4)), "edge_layer_fwd_t16")
+
     def edge_layer_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
         """fp32-FMA twin of edge_layer (cross-check only; FastEGNN.forward never calls it)."""
         N, E, A, Cn, Na = dims

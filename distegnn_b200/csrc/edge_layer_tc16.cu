@@ -1,4 +1,5 @@
-// Real<->real edge stage on the 5th-gen tensor cores — production kernel behind distegnn_edge_layer_fwd.
+// Real<->real edge stage on the 5th-gen tensor cores, thread-per-row flavour — behind distegnn_edge_layer_fwd_t16
+// (the production symbol distegnn_edge_layer_fwd runs the column-split flavour, edge_layer_cs.cu; this one is its twin).
 // Replaces reference models/FastEGNN.py:237-246 (coord2radial), 144-150 (edge_model), 169-177 (edge part of
 // coord_model_vel), 206 (edge part of node_model) and the scatter_add_ of :322-337 (twins models/basic.py:22-66).
 //
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) edge_layer_t16_kernel(const Ed
 
 }  // namespace degnn
 
-extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+extern "C" int distegnn_edge_layer_fwd_t16(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q,
                                        const float* layer_params, float* agg_m, float* agg_x, void* stream) {

@@ -167,6 +167,14 @@ DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A
                             const float *x4, const float *P, const float *Q,
                             const float *layer_params, float *agg_m, float *agg_x, void *stream);
 
+/* Same contract as distegnn_edge_layer_fwd: the thread-per-row tcgen05 kernel (16 warps per SM, 128 registers per
+ * thread; csrc/edge_layer_tc16.cu).  The production symbol runs the column-split flavour (two threads per row, 32
+ * warps per SM; csrc/edge_layer_cs.cu); this twin is kept for cross-checks and A/B timing. */
+DISTEGNN_API int distegnn_edge_layer_fwd_t16(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+                                             const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
+                                             const float* x4, const float* P, const float* Q,
+                                             const float* layer_params, float* agg_m, float* agg_x, void* stream);
+
 /* Same contract as distegnn_edge_layer_fwd, computed with fp32 FMA on the CUDA cores (no tensor cores).
  * Kept as an independent implementation for cross-checks of the tcgen05 kernel at sizes the CPU oracle
  * cannot reach; not used by FastEGNN.forward. */

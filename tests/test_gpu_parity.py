@@ -101,13 +101,14 @@ def test_edge_kernel_tensor_core_vs_fma_twin():
     x4[:, :3] = inp["node_loc"]
     for flags in (0, _lib.FLAG_NORMALIZE, _lib.FLAG_LAST):
         outs = []
-        for fn in (be.edge_layer_simt, be.edge_layer, be.edge_layer_tf32):
+        for fn in (be.edge_layer_simt, be.edge_layer, be.edge_layer_tf32, be.edge_layer_t16):
             agg_m, agg_x = torch.zeros(N, 64, device=dev()), torch.zeros(N, 4, device=dev())
             fn((N, E, 2, 8, 2), flags, row, col, ea, x4, P, Q, lp, None if flags & _lib.FLAG_LAST else agg_m,
                agg_x)
             torch.cuda.synchronize()
             outs.append((agg_m, agg_x))
-        for name, o in (("fp16-split", outs[1]), ("3xTF32", outs[2])):
+        for name, o in (("fp16-split column-split (production)", outs[1]), ("3xTF32", outs[2]),
+                        ("fp16-split thread-per-row", outs[3])):
             em = max_abs(o[0], outs[0][0]) / max(1e-9, float(outs[0][0].abs().max()))
             ex = max_abs(o[1], outs[0][1]) / max(1e-9, float(outs[0][1].abs().max()))
             print(f"flags {flags} {name}: rel err agg_m {em:.3e} agg_x {ex:.3e}")
@@ -135,7 +136,7 @@ def test_edge_kernel_fp16_range_rescue():
     x4 = torch.zeros(N, 4, device=dev())
     x4[:, :3] = inp["node_loc"]
     outs = []
-    for fn in (be.edge_layer_simt, be.edge_layer):
+    for fn in (be.edge_layer_simt, be.edge_layer, be.edge_layer_t16):
         agg_m, agg_x = torch.zeros(N, 64, device=dev()), torch.zeros(N, 4, device=dev())
         fn((N, E, 2, 3, 0), 0, row, col, ea, x4, P, Q, lp, agg_m, agg_x)
         torch.cuda.synchronize()
@@ -154,11 +155,15 @@ def test_edge_kernel_fp16_range_rescue():
 
     e_simt = (rowwise(outs[0][0], ref_m), rowwise(outs[0][1], ref_x))
     e_f16 = (rowwise(outs[1][0], ref_m), rowwise(outs[1][1], ref_x))
-    print(f"fp16 range rescue: row-wise rel err vs fp64  fp32-FMA twin {e_simt}  fp16-split tensor core {e_f16}")
-    assert e_f16[0] <= 2e-5
-    # Δx·φ has heavy cancellation at these magnitudes (fp32 FMA itself is at ~4e-5): the 22-bit operand split
-    # may lose up to 2 more bits than fp32's 24, never the range
-    assert e_f16[1] <= max(8 * e_simt[1], 2e-5) and e_f16[1] <= 1e-3
+    e_t16 = (rowwise(outs[2][0], ref_m), rowwise(outs[2][1], ref_x))
+    print(f"fp16 range rescue: row-wise rel err vs fp64  fp32-FMA twin {e_simt}  fp16-split tensor core: "
+          f"column-split {e_f16}  thread-per-row {e_t16}")
+    assert torch.isfinite(outs[2][0]).all() and torch.isfinite(outs[2][1]).all()
+    for e_k in (e_f16, e_t16):
+        assert e_k[0] <= 2e-5
+        # Δx·φ has heavy cancellation at these magnitudes (fp32 FMA itself is at ~4e-5): the 22-bit operand split
+        # may lose up to 2 more bits than fp32's 24, never the range
+        assert e_k[1] <= max(8 * e_simt[1], 2e-5) and e_k[1] <= 1e-3
 
 
 def test_edge_kernel_silu_batch_guard():
@@ -186,7 +191,7 @@ def test_edge_kernel_silu_batch_guard():
     x4 = torch.zeros(N, 4, device=dev())
     x4[:, :3] = inp["node_loc"]
     outs = []
-    for fn in (be.edge_layer_simt, be.edge_layer):
+    for fn in (be.edge_layer_simt, be.edge_layer, be.edge_layer_t16):
         agg_m, agg_x = torch.zeros(N, 64, device=dev()), torch.zeros(N, 4, device=dev())
         fn((N, E, 2, 3, 0), 0, row, col, ea, x4, P, Q, lp, agg_m, agg_x)
         torch.cuda.synchronize()
@@ -195,12 +200,13 @@ def test_edge_kernel_silu_batch_guard():
                                                                                       dtype=torch.float64)
     ShadowBackend().edge_layer((N, E, 2, 3, 0), 0, row, col, ea.double(), x4.double(), P.double(), Q.double(),
                                lp.double(), ref_m, ref_x)
-    assert torch.isfinite(outs[1][0]).all() and torch.isfinite(outs[1][1]).all()
-    e_m = float((outs[1][0].double() - ref_m).abs().max() / ref_m.abs().max())
-    e_x = float((outs[1][1].double() - ref_x[:, :3]).abs().max() / ref_x[:, :3].abs().max())
     e_m0 = float((outs[0][0].double() - ref_m).abs().max() / ref_m.abs().max())
-    print(f"silu batch guard: rel err vs fp64  agg_m {e_m:.2e} (fp32-FMA twin {e_m0:.2e})  agg_x {e_x:.2e}")
-    assert e_m <= 5e-6 and e_x <= 5e-5
+    for name, o in (("column-split", outs[1]), ("thread-per-row", outs[2])):
+        assert torch.isfinite(o[0]).all() and torch.isfinite(o[1]).all()
+        e_m = float((o[0].double() - ref_m).abs().max() / ref_m.abs().max())
+        e_x = float((o[1].double() - ref_x[:, :3]).abs().max() / ref_x[:, :3].abs().max())
+        print(f"silu batch guard [{name}]: rel err vs fp64  agg_m {e_m:.2e} (fp32-FMA twin {e_m0:.2e})  agg_x {e_x:.2e}")
+        assert e_m <= 5e-6 and e_x <= 5e-5
 
 
 @pytest.mark.parametrize("C,B", [(8, 1), (5, 1), (3, 7)])
