@@ -83,6 +83,24 @@ class CudaBackend:
                                                self._s(x4)), "edge_layer_fwd")
         self.launches += 1 if E else 0
 
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
+        """Backward of edge_layer: accumulates into g_P, g_Q, g_x4 and the parameter-gradient block g_lp."""
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_bwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea), ptr(x4), ptr(P),
+                                               ptr(Q), ptr(lp), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P), ptr(g_Q),
+                                               ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd")
+        self.launches += 1 if E else 0
+
+    def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
+                          g_G, g_Xv, g_lp) -> None:
+        """Backward of virtual_layer: writes g_Hn, g_xv; accumulates into g_G, g_Xv and the parameter-gradient block."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_layer_bwd(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn), ptr(Xv),
+                                                  ptr(G), ptr(lp), ptr(wT), ptr(g_agg_v), ptr(g_trans_v), ptr(g_vsum),
+                                                  ptr(g_Hn), ptr(g_xv), ptr(g_G), ptr(g_Xv), ptr(g_lp), self._s(x4)),
+              "virtual_layer_bwd")
+        self.launches += 1 if N else 0
+
     def edge_layer_t16(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
         """thread-per-row tcgen05 twin of edge_layer (cross-check / A-B timing only)."""
         N, E, A, Cn, Na = dims

@@ -241,6 +241,30 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[8][4], const float* As, c
     }
 }
 
+// same with the [64][64] weight matrix read straight from global memory (L1/L2 resident, 16 KB): used by the backward
+// kernels, whose shared memory is taken by activation / gradient tiles
+__device__ __forceinline__ void gemm_tile_g(float (&acc)[8][4], const float* As, const float* __restrict__ Wg, int ty,
+                                            int tx) {
+#pragma unroll 2
+    for (int k4 = 0; k4 < 16; ++k4) {
+        float4 w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = ldg4(Wg + (4 * k4 + j) * H + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 a = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * LDA + 4 * k4);
+            acc[i][0] = fmaf(a.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, w[0].y, acc[i][1]);
+            acc[i][2] = fmaf(a.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, w[0].w, acc[i][3]);
+            acc[i][0] = fmaf(a.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, w[1].y, acc[i][1]);
+            acc[i][2] = fmaf(a.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, w[1].w, acc[i][3]);
+            acc[i][0] = fmaf(a.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, w[2].y, acc[i][1]);
+            acc[i][2] = fmaf(a.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, w[2].w, acc[i][3]);
+            acc[i][0] = fmaf(a.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, w[3].y, acc[i][1]);
+            acc[i][2] = fmaf(a.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, w[3].w, acc[i][3]);
+        }
+    }
+}
+
 // act = SiLU(acc + bias) written back to the activation tile (the A operand of the next GEMM).
 // Caller must __syncthreads() before (all reads of As done) and after.
 __device__ __forceinline__ void bias_silu_to_tile(const float (&acc)[8][4], float4 b, float* As, int ty,

@@ -70,10 +70,16 @@ class E_GCL_vel(nn.Module):
 # packing of one layer's weights into the flat block the kernels read (include/distegnn_b200.h)
 # --------------------------------------------------------------------------------------------------
 def pack_layer_params(g: nn.Module, A: int, Cn: int, Na: int, device, offs: Dict[str, int],
-                      total: int) -> Tensor:
-    buf = torch.zeros(total, dtype=torch.float32, device=device)
+                      total: int, differentiable: bool = False) -> Tensor:
+    """Flat parameter block of one layer.  `differentiable=True` (training) builds it with torch.cat from the live
+    parameters, so that the gradient of the block flows back to the nn.Parameters through autograd."""
+    buf = None if differentiable else torch.zeros(total, dtype=torch.float32, device=device)
+    pieces: List[Tuple[int, Tensor]] = []
 
     def put(name: str, t: Tensor) -> None:
+        if differentiable:
+            pieces.append((offs[name], t.to(device=device, dtype=torch.float32).reshape(-1)))
+            return
         t = t.detach().to(device=device, dtype=torch.float32).reshape(-1)
         buf[offs[name]:offs[name] + t.numel()] = t
 
@@ -99,7 +105,17 @@ def pack_layer_params(g: nn.Module, A: int, Cn: int, Na: int, device, offs: Dict
     put("N_W2", g.node_mlp[2].weight.t()); put("N_B2", g.node_mlp[2].bias)
     put("M_W1", g.node_mlp_virtual[0].weight.t()); put("M_B1", g.node_mlp_virtual[0].bias)
     put("M_W2", g.node_mlp_virtual[2].weight.t()); put("M_B2", g.node_mlp_virtual[2].bias)
-    return buf
+    if not differentiable:
+        return buf
+    parts, pos = [], 0
+    for off, t in sorted(pieces, key=lambda p: p[0]):
+        if off > pos:
+            parts.append(torch.zeros(off - pos, dtype=torch.float32, device=device))
+        parts.append(t)
+        pos = off + t.numel()
+    if pos < total:
+        parts.append(torch.zeros(total - pos, dtype=torch.float32, device=device))
+    return torch.cat(parts)
 
 
 class _GraphCache:
@@ -233,10 +249,7 @@ class FastEGNN(nn.Module):
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, node_feat, node_loc, node_vel, loc_mean, edge_index, data_batch, edge_attr=None,
                 node_attr=None) -> Tuple[Tensor, Tensor]:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned_grad:
-            warnings.warn("distegnn_b200.FastEGNN: the fused CUDA path is forward-only in this release; "
-                          "outputs are detached (backward = SURVEY §8 f-1).", stacklevel=2)
-            self._warned_grad = True
+        training_path = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         dev = node_loc.device
         be = self._get_backend(dev)
         A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
@@ -258,6 +271,9 @@ class FastEGNN(nn.Module):
         f32 = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) \
             else t.detach().to(dtype=torch.float32).contiguous()
 
+        if training_path:
+            return self._forward_autograd(be, dev, (N, E, B, K), f32, node_feat, node_loc, node_vel, loc_mean,
+                                          edge_index, data_batch, edge_attr, node_attr)
         with torch.no_grad():
             pk = self._packed_params(dev)
             rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
@@ -272,6 +288,73 @@ class FastEGNN(nn.Module):
             ws = self._alloc_workspace(dev, N, B, K)
             out, Xv = self._run(be, pk, dims, args, ws)
         return out, Xv
+
+    # ---- training path -----------------------------------------------------------------
+    def _forward_autograd(self, be, dev, dims, f32, node_feat, node_loc, node_vel, loc_mean, edge_index, data_batch,
+                          edge_attr, node_attr) -> Tuple[Tensor, Tensor]:
+        """Forward with a backward: same kernels as the inference path, per-layer activations kept (N-sized only:
+        nothing of size [E,.] or [N,C,.] is ever stored), gradients through `_FastEGNNFunction`.  Inputs are treated
+        as constants (the reference trains weights only: utils/train.py:149-158)."""
+        A, Cn, Na = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf
+        N, E, B, K = dims
+        offs, total = _lib.param_layout(A, Cn, Na)
+        lps = [pack_layer_params(getattr(self, "gcl_%d" % i), A, Cn, Na, dev, offs, total, differentiable=True)
+               for i in range(self.n_layers)]
+        emb_wt = self.embedding_in.weight.t().contiguous().to(device=dev, dtype=torch.float32)
+        emb_b = self.embedding_in.bias.to(device=dev, dtype=torch.float32)
+        hv0 = self.virtual_node_feat[0].t().contiguous().to(device=dev, dtype=torch.float32)          # [C,64]
+        with torch.no_grad():
+            rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
+            ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
+            args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
+                        loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
+                        data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
+        return _FastEGNNFunction.apply(self, be, dims, args, emb_wt, emb_b, hv0, *lps)
+
+    def _run_saving(self, be, dims, a: Dict[str, Tensor], emb_wt, emb_b, hv0, layers: List[Tensor]):
+        """`_run` with fresh buffers per layer; returns (out, Xv_L, saved state for the backward)."""
+        A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
+        N, E, B, K = dims
+        dev = a["node_loc"].device
+        new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        zeros = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        L = self.n_layers
+        base = _lib.FLAG_NORMALIZE if self.normalize else 0
+        Xv = a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn).contiguous()
+        Hv = hv0.unsqueeze(0).expand(B, Cn, H).contiguous()
+        h, x4, batch32, P, Q, Hn = new(N, H), new(N, 4), new(N, dt=torch.int32), new(N, H), new(N, H), new(N, H)
+        vsum = zeros(B, K)
+        be.embed((N, B, F, A, Cn, Na), a["node_feat"], a["node_loc"], a["data_batch"], emb_wt, emb_b,
+                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
+        st = dict(batch32=batch32, vsum_init=vsum, layers=[])
+        if L == 0:
+            return a["node_loc"].clone(), Xv, st
+        self._sync_virtual(vsum)
+        G = new(B, Cn, H)
+        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
+        out = None
+        for i in range(L):
+            last = i == L - 1
+            flags = base | (_lib.FLAG_LAST if last else 0)
+            lp, lp_next = layers[i], (None if last else layers[i + 1])
+            agg_x, trans_v, vs = zeros(N, 4), new(N, 4), zeros(B, K)
+            agg_m = None if last else zeros(N, H)
+            agg_v = None if last else new(N, H)
+            be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp, agg_m, agg_x)
+            be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vs)
+            x4n = new(N, 4)
+            hn, Pn, Qn, Hnn = (None,) * 4 if last else (new(N, H), new(N, H), new(N, H), new(N, H))
+            out = new(N, 3) if last else None
+            be.node_layer((N, B, A, Cn, Na), flags, a["rowptr"], batch32, h, x4, a["node_vel"], a["attr"], agg_m,
+                          agg_x, agg_v, trans_v, lp, lp_next, hn, x4n, Pn, Qn, Hnn, out, vs)
+            self._sync_virtual(vs)
+            st["layers"].append(dict(h=h, x4=x4, P=P, Q=Q, Hn=Hn, Xv=Xv, Hv=Hv, G=G, agg_m=agg_m, agg_x=agg_x,
+                                     agg_v=agg_v, trans_v=trans_v, vsum=vs, flags=flags))
+            Xv, Hv = Xv.clone(), (Hv if last else Hv.clone())
+            Gn = None if last else new(B, Cn, H)
+            be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vs, Xv, Hv, lp, lp_next, Gn)
+            h, x4, P, Q, Hn, G = hn, x4n, Pn, Qn, Hnn, Gn
+        return out, Xv, st
 
     # ---- device work ---------------------------------------------------------------------------
     def _alloc_workspace(self, dev, N: int, B: int, K: int) -> Dict[str, Tensor]:
@@ -356,3 +439,121 @@ class FastEGNN(nn.Module):
         ent[0].replay()
         be.launches += ent[2]
         return ent[1]["out"].clone(), ent[1]["Xv"].clone()
+
+
+class _FastEGNNFunction(torch.autograd.Function):
+    """Autograd node of the fused path.  forward = the sm_100a kernels (FastEGNN._run_saving); backward = per layer, in
+    reverse: virtual-node update and node stage (dense [N,64] layers: torch recompute + autograd, _dense_stages.py),
+    ONE packed all-reduce of the statistics' gradient (the reference's _AllReduce.backward, FastEGNN.py:19-21, issues
+    one per aggregate), then the hand-written real<->virtual and per-edge backward kernels (csrc/*_bwd.cu)."""
+
+    @staticmethod
+    def forward(ctx, model, be, dims, a, emb_wt, emb_b, hv0, *lps):
+        layers = [lp.detach().contiguous() for lp in lps]
+        out, Xv, st = model._run_saving(be, dims, a, emb_wt.detach().contiguous(), emb_b.detach().contiguous(),
+                                        hv0.detach().contiguous(), layers)
+        ctx.model, ctx.be, ctx.dims, ctx.a, ctx.st = model, be, dims, a, st
+        ctx.params = (emb_wt.detach(), emb_b.detach(), hv0.detach(), layers)
+        return out, Xv
+
+    @staticmethod
+    def backward(ctx, g_out, g_Xv_out):
+        from . import _dense_stages as ds
+        model, be, a, st = ctx.model, ctx.be, ctx.a, ctx.st
+        N, E, B, K = ctx.dims
+        A, Cn, Na = model.edge_attr_nf, model.virtual_channels, model.node_attr_nf
+        emb_wt, emb_b, hv0, layers = ctx.params
+        L = len(layers)
+        dev = emb_wt.device
+        offs, total = _lib.param_layout(A, Cn, Na)
+        zeros = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g_lps = [zeros(total) for _ in range(L)]
+        g_emb_wt, g_emb_b, g_hv0 = torch.zeros_like(emb_wt), torch.zeros_like(emb_b), torch.zeros_like(hv0)
+        if L == 0:
+            return (None, None, None, None, g_emb_wt, g_emb_b, g_hv0)
+        batch = a["data_batch"]
+        deg = (a["rowptr"][1:] - a["rowptr"][:-1]).clamp(min=1).to(torch.float32).unsqueeze(1)
+        attr = a["attr"]
+
+        def leaf(t):
+            return t.detach().requires_grad_(True)
+
+        def grads(outs, gouts, ins):
+            pairs = [(o, g) for o, g in zip(outs, gouts) if o is not None and g is not None]
+            res = torch.autograd.grad([o for o, _ in pairs], ins, [g for _, g in pairs], allow_unused=True)
+            return [torch.zeros_like(i) if r is None else r for r, i in zip(res, ins)]
+
+        g_x = g_out.contiguous().to(torch.float32) if g_out is not None else zeros(N, 3)
+        g_Xv = g_Xv_out.contiguous().to(torch.float32) if g_Xv_out is not None else zeros(B, 3, Cn)
+        g_Hv = g_G = g_h = g_P = g_Q = g_Hn = None
+        for i in reversed(range(L)):
+            S = st["layers"][i]
+            last = i == L - 1
+            lp, lp_next = layers[i], (None if last else layers[i + 1])
+            # ---- 1. virtual-node update: (g_Xv', g_Hv', g_G') -> g_vsum, g_Xv, g_Hv, parameter gradients ----------------
+            with torch.enable_grad():
+                vs, Xl, Hl, lpl = leaf(S["vsum"]), leaf(S["Xv"]), leaf(S["Hv"]), leaf(lp)
+                lpn = None if last else leaf(lp_next)
+                Xn, Hvn, Gn = ds.virtual_update_stage(vs, Xl, Hl, ds.field_views(lpl, A, Cn, Na),
+                                                      None if last else ds.field_views(lpn, A, Cn, Na), False, Cn)
+                ins = [vs, Xl, Hl, lpl] + ([] if last else [lpn])
+                r = grads([Xn, Hvn, Gn], [g_Xv, g_Hv, g_G], ins)
+            g_vsum, g_Xv_i, g_Hv_i = r[0].contiguous(), r[1], r[2]
+            g_lps[i] += r[3]
+            if not last:
+                g_lps[i + 1] += r[4]
+            if model.world_size > 1:                     # _AllReduce.backward (FastEGNN.py:19-21), one packed call
+                import torch.distributed as dist
+                dist.all_reduce(g_vsum, op=dist.ReduceOp.SUM, group=model.process_group)
+            # ---- 2. node stage: (g_x', g_h', g_P', g_Q', g_Hn') -> g_h, g_x, g_agg_*, g_trans_v, parameter gradients -----
+            with torch.enable_grad():
+                hl, xl = leaf(S["h"]), leaf(S["x4"][:, :3])
+                axl, tvl = leaf(S["agg_x"][:, :3]), leaf(S["trans_v"][:, :3])
+                aml = None if last else leaf(S["agg_m"])
+                avl = None if last else leaf(S["agg_v"])
+                lpl = leaf(lp)
+                lpn = None if last else leaf(lp_next)
+                xn, hn, Pn, Qn, Hnn = ds.node_stage(hl, xl, a["node_vel"], attr, aml, axl, avl, tvl, deg,
+                                                    ds.field_views(lpl, A, Cn, Na),
+                                                    None if last else ds.field_views(lpn, A, Cn, Na))
+                ins = [hl, xl, axl, tvl, lpl] + ([] if last else [aml, avl, lpn])
+                r = grads([xn, hn, Pn, Qn, Hnn], [g_x + g_vsum[batch, 0:3], g_h, g_P, g_Q, g_Hn], ins)
+            g_h_i, g_x_i = r[0], r[1]
+            g_agg_x, g_trans_v = zeros(N, 4), zeros(N, 4)
+            g_agg_x[:, :3], g_trans_v[:, :3] = r[2], r[3]
+            g_lps[i] += r[4]
+            g_agg_m = g_agg_v = None
+            if not last:
+                g_agg_m, g_agg_v = r[5].contiguous(), r[6].contiguous()
+                g_lps[i + 1] += r[7]
+            # ---- 3. real<->virtual stage (CUDA) ------------------------------------------------------------------------
+            wT = torch.stack([lp[offs[k]:offs[k] + H * H].view(H, H).t().contiguous() for k in ("V_W2", "V_WXV", "V_WX")])
+            g_Hn_i, g_xv = torch.empty(N, H, device=dev), torch.empty(N, 4, device=dev)
+            g_G_i, g_Xv_acc = zeros(B, Cn, H), g_Xv_i.contiguous().clone()
+            be.virtual_layer_bwd((N, B, A, Cn, Na), S["flags"], st["batch32"], S["x4"], S["Hn"], S["Xv"], S["G"], lp, wT,
+                                 g_agg_v, g_trans_v, g_vsum, g_Hn_i, g_xv, g_G_i, g_Xv_acc, g_lps[i])
+            # ---- 4. per-edge stage (CUDA) --------------------------------------------------------------------------------
+            g_P_i, g_Q_i, g_x4e = zeros(N, H), zeros(N, H), zeros(N, 4)
+            be.edge_layer_bwd((N, E, A, Cn, Na), S["flags"], a["row"], a["col"], a["ea"], S["x4"], S["P"], S["Q"], lp,
+                              g_agg_m, g_agg_x, g_P_i, g_Q_i, g_x4e, g_lps[i])
+            g_x = g_x_i + g_xv[:, :3] + g_x4e[:, :3]
+            g_h, g_P, g_Q, g_Hn = g_h_i, g_P_i, g_Q_i, g_Hn_i
+            g_Xv, g_Hv, g_G = g_Xv_acc, g_Hv_i, g_G_i
+        # ---- initial virtual state: G_0 = f(Hv_0 = hv0, X_0 = loc_mean, x̄_0; layer-0 parameters) -------------------------
+        with torch.enable_grad():
+            hv0l, lp0 = leaf(hv0), leaf(layers[0])
+            Xv0 = a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn)
+            Hv0 = hv0l.unsqueeze(0).expand(B, Cn, H)
+            _, Hv0o, G0 = ds.virtual_update_stage(st["vsum_init"], Xv0, Hv0, None, ds.field_views(lp0, A, Cn, Na), True, Cn)
+            r = grads([Hv0o, G0], [g_Hv, g_G], [hv0l, lp0])
+        g_hv0 += r[0]
+        g_lps[0] += r[1]
+        # ---- embedding + layer-0 projections ----------------------------------------------------------------------------------
+        with torch.enable_grad():
+            wl, bl, lp0 = leaf(emb_wt), leaf(emb_b), leaf(layers[0])
+            h0, P0, Q0, Hn0 = ds.embed_stage(a["node_feat"], wl, bl, ds.field_views(lp0, A, Cn, Na))
+            r = grads([h0, P0, Q0, Hn0], [g_h, g_P, g_Q, g_Hn], [wl, bl, lp0])
+        g_emb_wt += r[0]
+        g_emb_b += r[1]
+        g_lps[0] += r[2]
+        return (None, None, None, None, g_emb_wt, g_emb_b, g_hv0, *g_lps)

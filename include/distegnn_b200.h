@@ -167,6 +167,31 @@ DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A
                             const float *x4, const float *P, const float *Q,
                             const float *layer_params, float *agg_m, float *agg_x, void *stream);
 
+/* Backward of distegnn_edge_layer_fwd (in the reference: autograd through models/FastEGNN.py:144-150,
+ * 169-177, 206, 237-246, 322-337).  Nothing of size [E,.] is kept from the forward pass: every 128-edge tile is
+ * recomputed.  Inputs: the forward inputs plus g_agg_m [N,64] (gradient w.r.t. the SUM agg_m; may be NULL with
+ * FLAG_LAST) and g_agg_x [N,4] (w.r.t. the SUM agg_x).  Outputs are ACCUMULATED (+=): g_P, g_Q [N,64], g_x4 [N,4]
+ * (both edge endpoints; the normalisation norm is detached as in :243) and g_layer_params, a buffer with the layout
+ * of the parameter block (fields E_W1R, E_W1E, E_W2, E_B2, E_WC, E_BC, E_W3 are written). */
+DISTEGNN_API int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+                                         const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
+                                         const float* x4, const float* P, const float* Q, const float* layer_params,
+                                         const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
+                                         float* g_x4, float* g_layer_params, void* stream);
+
+/* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
+ * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile.  Inputs: the forward inputs, wT = the three
+ * 64x64 matrices V_W2, V_WXV, V_WX of the parameter block TRANSPOSED ([3][64][64], wT[m][n*64+k] = W_m[k*64+n]), and the
+ * upstream gradients g_agg_v [N,64] (NULL with FLAG_LAST), g_trans_v [N,4], g_vsum [B,K] (entries [4:] are read; already
+ * summed over the partitions).  g_Hn [N,64] and g_xv [N,4] are WRITTEN; g_G [B,C,64], g_Xv [B,3,C] and the parameter
+ * gradients (V_W1R, V_W2, V_B2, V_WXV, V_BXV, V_W3XV, V_WX, V_BX, V_W3X of a parameter-layout buffer) are accumulated. */
+DISTEGNN_API int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                                            const int32_t* batch32, const float* x4, const float* Hn, const float* Xv,
+                                            const float* G, const float* layer_params, const float* wT,
+                                            const float* g_agg_v, const float* g_trans_v, const float* g_vsum,
+                                            float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
+                                            void* stream);
+
 /* Same contract as distegnn_edge_layer_fwd: the thread-per-row tcgen05 kernel (16 warps per SM, 128 registers per
  * thread; csrc/edge_layer_tc16.cu).  The production symbol runs the column-split flavour (two threads per row, 32
  * warps per SM; csrc/edge_layer_cs.cu); this twin is kept for cross-checks and A/B timing. */

@@ -610,3 +610,95 @@ def test_full_size_config5_properties():
     assert max_abs(out, out_p) <= 2e-6 * scale and max_abs(X, X_p) <= 2e-6 * scale
     assert max_abs(out @ R + t, out_r) <= 1e-4
     assert max_abs(X.permute(0, 2, 1) @ R + t, X_r.permute(0, 2, 1)) <= 1e-4
+
+
+# ---- backward kernels: each stage against torch.autograd on its float64 restatement --------------------
+def _rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,A", [(0, 2), (_lib.FLAG_NORMALIZE, 2), (_lib.FLAG_LAST, 2), (0, 0)])
+def test_edge_stage_backward(flags, A):
+    from distegnn_b200.backend import cuda_backend
+    from tests import shadow_autograd as sa
+    be = cuda_backend()
+    w = synth.WORKLOADS["water3d_10k"]
+    inp = to_dev(synth.make_partitions(w, n_nodes=6_000, seed=21)[0])
+    C, Na = 3, 0
+    sd = orc.init_state_dict(2, Na, A, 64, C, 1, seed=5, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=1), sd)
+    lp = m._packed_params(dev())["layers"][0]
+    N, E = inp["node_loc"].shape[0], inp["edge_index"].shape[1]
+    rowptr, row, col, perm = be.build_csr(inp["edge_index"], N)
+    ea = be.gather_rows(inp["edge_attr"], perm)[:, :A].contiguous() if A else None
+    g = torch.Generator().manual_seed(6)
+    P, Q = torch.randn(N, 64, generator=g).to(dev()), torch.randn(N, 64, generator=g).to(dev())
+    x4 = torch.zeros(N, 4, device=dev())
+    x4[:, :3] = inp["node_loc"]
+    g_m = torch.randn(N, 64, generator=g).to(dev())
+    g_x = torch.zeros(N, 4, device=dev())
+    g_x[:, :3] = torch.randn(N, 3, generator=g).to(dev())
+    last = bool(flags & _lib.FLAG_LAST)
+    # reference: autograd in float64
+    Pd, Qd, xd, lpd = (t.double().requires_grad_(True) for t in (P, Q, x4[:, :3], lp))
+    am, ax = sa.edge_stage((N, E, A, C, Na), flags, row, col, ea.double() if A else None, xd, Pd, Qd, lpd)
+    loss = (ax * g_x[:, :3].double()).sum() + (0 if last else (am * g_m.double()).sum())
+    rP, rQ, rx, rlp = torch.autograd.grad(loss, (Pd, Qd, xd, lpd))
+    # kernel
+    gP, gQ, gx4, glp = (torch.zeros_like(t) for t in (P, Q, x4, lp))
+    be.edge_layer_bwd((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, lp, None if last else g_m, g_x, gP, gQ, gx4, glp)
+    torch.cuda.synchronize()
+    errs = dict(P=_rel(gP, rP), Q=_rel(gQ, rQ), x=_rel(gx4[:, :3], rx), params=_rel(glp, rlp))
+    offs, _ = _lib.param_layout(A, C, Na)
+    for k in ("E_W1R", "E_W1E", "E_W2", "E_B2", "E_WC", "E_BC", "E_W3"):
+        n = {"E_W1E": A * 64, "E_W2": 4096, "E_WC": 4096}.get(k, 64)
+        if n:
+            errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
+    print(f"edge stage backward flags={flags} A={A}: rel err vs float64 autograd {errs}")
+    assert max(errs.values()) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,B,last", [(8, 1, False), (3, 5, False), (5, 1, True)])
+def test_virtual_stage_backward(C, B, last):
+    from distegnn_b200.backend import cuda_backend
+    from tests import shadow_autograd as sa
+    be = cuda_backend()
+    A, Na, N = 2, 0, 5_003
+    sd = orc.init_state_dict(2, Na, A, 64, C, 1, seed=8, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=1), sd)
+    lp = m._packed_params(dev())["layers"][0]
+    offs, _ = _lib.param_layout(A, C, Na)
+    g = torch.Generator().manual_seed(9)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev())
+    batch = torch.sort(torch.randint(0, B, (N,), generator=g)).values.to(torch.int32).to(dev())
+    x4 = torch.zeros(N, 4, device=dev())
+    x4[:, :3] = rnd(N, 3)
+    Hn, Xv, G = rnd(N, 64), rnd(B, 3, C), rnd(B, C, 64)
+    K = 4 + 3 * C + 64 * C
+    g_aggv, g_tv, g_vsum = rnd(N, 64), torch.zeros(N, 4, device=dev()), rnd(B, K)
+    g_tv[:, :3] = rnd(N, 3)
+    if last:
+        g_vsum[:, 4 + 3 * C:] = 0
+    flags = _lib.FLAG_LAST if last else 0
+    # reference
+    xd, Hd, Xd, Gd, lpd = (t.double().requires_grad_(True) for t in (x4[:, :3], Hn, Xv, G, lp))
+    av, tv, tail = sa.virtual_stage((N, B, A, C, Na), flags, batch, xd, Hd, Xd, Gd, lpd)
+    loss = (tv * g_tv[:, :3].double()).sum() + (tail * g_vsum[:, 4:].double()).sum()
+    if not last:
+        loss = loss + (av * g_aggv.double()).sum()
+    rx, rH, rX, rG, rlp = torch.autograd.grad(loss, (xd, Hd, Xd, Gd, lpd))
+    # kernel
+    wT = torch.stack([lp[offs[k]:offs[k] + 4096].view(64, 64).t().contiguous() for k in ("V_W2", "V_WXV", "V_WX")])
+    gHn, gxv = torch.empty(N, 64, device=dev()), torch.empty(N, 4, device=dev())
+    gG, gXv, glp = torch.zeros_like(G), torch.zeros_like(Xv), torch.zeros_like(lp)
+    be.virtual_layer_bwd((N, B, A, C, Na), flags, batch, x4, Hn, Xv, G, lp, wT, None if last else g_aggv, g_tv, g_vsum,
+                         gHn, gxv, gG, gXv, glp)
+    torch.cuda.synchronize()
+    errs = dict(Hn=_rel(gHn, rH), x=_rel(gxv[:, :3], rx), G=_rel(gG, rG), Xv=_rel(gXv, rX))
+    for k in ("V_W1R", "V_W2", "V_B2", "V_WXV", "V_BXV", "V_W3XV", "V_WX", "V_BX", "V_W3X"):
+        n = 4096 if k in ("V_W2", "V_WXV", "V_WX") else 64
+        errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
+    print(f"virtual stage backward C={C} B={B} last={last}: rel err vs float64 autograd {errs}")
+    assert max(errs.values()) <= 2e-5
