@@ -120,7 +120,7 @@ def _layer(sd: StateDict, pfx: str, parts: List[dict], X: Tensor, Hv: Tensor, C:
         dx = x[row] - x[col]
         radial = torch.sum(dx ** 2, 1, keepdim=True)
         if normalize:
-            dx = dx / (torch.sqrt(radial) + 1e-8)
+            dx = dx / (torch.sqrt(radial).detach() + 1e-8)      # norm detached (FastEGNN.py:243): matters for autograd
         # virtual geometry, FastEGNN.py:252-253
         dX = X[b] - x.unsqueeze(-1)                                    # [N,3,C]
         vr = torch.norm(dX, p=2, dim=1, keepdim=True)                  # [N,1,C]

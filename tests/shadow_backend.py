@@ -143,3 +143,40 @@ class ShadowBackend:
         mX = torch.einsum("bdi,bdj->bij", Z, Z)                    # [B,C,C]
         # G[b,c,:] = Hv[b,c,:]·W1v_V + Σ_j m_X[b,j,c]·W1v_M[j,:] + b1v
         G.copy_(Hv @ g["V_W1V"] + torch.einsum("bjc,jn->bcn", mX, g["V_W1M"]) + g["V_B1"])
+
+    # ---- backward stand-ins (torch.autograd over tests/shadow_autograd.py): same accumulate / write contracts as
+    # distegnn_edge_layer_bwd / distegnn_virtual_layer_bwd, so that FastEGNN's training path can run on CPU ---------
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp):
+        from tests import shadow_autograd as sa
+        N, E, A, C, Na = dims
+        if E == 0:
+            return
+        with torch.enable_grad():
+            Pl, Ql, xl, lpl = (t.detach().clone().requires_grad_(True) for t in (P, Q, x4[:, :3], lp))
+            am, ax = sa.edge_stage(dims, flags, row, col, ea, xl, Pl, Ql, lpl)
+            loss = (ax * g_agg_x[:, :3]).sum()
+            if g_agg_m is not None and not flags & _lib.FLAG_LAST:
+                loss = loss + (am * g_agg_m).sum()
+            gP, gQ, gx, glp = torch.autograd.grad(loss, (Pl, Ql, xl, lpl), allow_unused=True)
+        g_P += gP
+        g_Q += gQ
+        g_x4[:, :3] += gx
+        g_lp += glp
+
+    def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
+                          g_G, g_Xv, g_lp):
+        from tests import shadow_autograd as sa
+        N, B, A, C, Na = dims
+        with torch.enable_grad():
+            xl, Hl, Xl, Gl, lpl = (t.detach().clone().requires_grad_(True) for t in (x4[:, :3], Hn, Xv, G, lp))
+            av, tv, tail = sa.virtual_stage(dims, flags, batch32, xl, Hl, Xl, Gl, lpl)
+            loss = (tv * g_trans_v[:, :3]).sum() + (tail[:, :3 * C] * g_vsum[:, 4:4 + 3 * C]).sum()
+            if g_agg_v is not None and not flags & _lib.FLAG_LAST:
+                loss = loss + (av * g_agg_v).sum() + (tail[:, 3 * C:] * g_vsum[:, 4 + 3 * C:]).sum()
+            gx, gH, gX, gG, glp = torch.autograd.grad(loss, (xl, Hl, Xl, Gl, lpl), allow_unused=True)
+        g_Hn.copy_(gH)
+        g_xv.zero_()
+        g_xv[:, :3] = gx
+        g_G += gG
+        g_Xv += gX
+        g_lp += glp

@@ -702,3 +702,93 @@ def test_virtual_stage_backward(C, B, last):
         errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
     print(f"virtual stage backward C={C} B={B} last={last}: rel err vs float64 autograd {errs}")
     assert max(errs.values()) <= 2e-5
+
+
+# ---- the whole training path on the GPU: forward kernels + backward kernels + dense stages, against the reference's own
+# gradients (fixtures from oracle/make_golden_grads.py) and against float64 autograd through the oracle -------------------
+def _param_grad_errors(model, ref_grads):
+    errs, dead = {}, 0
+    for k, p in model.named_parameters():
+        ref = ref_grads[k]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        if float(ref.abs().max()) == 0.0:
+            assert float(g.abs().max()) == 0.0, k
+            dead += 1
+            continue
+        errs[k] = float((g.detach().cpu().double() - ref.double()).abs().max() / ref.double().abs().max())
+    return errs, dead
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_training_path_gradients_against_reference_fixtures(name):
+    import numpy as np
+    from tests.helpers import GOLDEN
+    import os
+    z, kw, sd = load_golden(name)
+    zg = np.load(os.path.join(GOLDEN, name + ".grads.npz"))
+    inp = to_dev(golden_inputs(z))
+    m = cuda_model(kw, sd).train()
+    out, X = m(**inp)
+    assert out.requires_grad and X.requires_grad
+    loss = (out * torch.from_numpy(zg["cot.out"]).float().to(dev())).sum() + \
+           (X * torch.from_numpy(zg["cot.X"]).float().to(dev())).sum()
+    loss.backward()
+    assert abs(float(loss) - float(zg["loss"])) <= 1e-4 * max(1.0, abs(float(zg["loss"])))
+    errs, dead = _param_grad_errors(m, {k: torch.from_numpy(zg["grad." + k]) for k, _ in m.named_parameters()})
+    worst = max(errs, key=errs.get)
+    print(f"{name}: training-path gradients vs reference fp64: worst {worst} {errs[worst]:.2e}; {dead} dead parameters")
+    assert errs[worst] <= 2e-4          # the reference's own fp32 run is within 3e-5 of its fp64 run on these cases
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wname,n,normalize", [("fluid113k", 4000, False), ("water3d_10k", 3000, True)])
+def test_training_path_gradients_against_oracle_autograd(wname, n, normalize):
+    w = synth.WORKLOADS[wname]
+    host = synth.make_partitions(w, n_nodes=n, seed=31)[0]
+    F, Na, A, C = w.node_feat_nf, w.node_attr_nf, 2, w.virtual_channels
+    sd = orc.init_state_dict(F, Na, A, 64, C, 3, seed=12, coord_gain=0.05)
+    kw = dict(node_feat_nf=F, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=3, normalize=normalize)
+    g = torch.Generator().manual_seed(13)
+    cot_out, cot_X = torch.randn(n, 3, generator=g), torch.randn(1, 3, C, generator=g)
+    # oracle, float64, CPU autograd
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    inp64 = {k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in host.items()}
+    o64, X64 = orc.forward(sd64, **inp64, normalize=normalize)
+    l64 = (o64 * cot_out.double()).sum() + (X64 * cot_X.double()).sum()
+    keys = list(sd64)
+    ref = dict(zip(keys, torch.autograd.grad(l64, [sd64[k] for k in keys], allow_unused=True)))
+    ref = {k: (v if v is not None else torch.zeros_like(sd64[k])) for k, v in ref.items()}
+    # product
+    m = cuda_model(kw, sd).train()
+    out, X = m(**to_dev(host))
+    loss = (out * cot_out.to(dev())).sum() + (X * cot_X.to(dev())).sum()
+    loss.backward()
+    errs, dead = _param_grad_errors(m, ref)
+    worst = max(errs, key=errs.get)
+    print(f"{wname} n={n} normalize={normalize}: gradients vs oracle fp64 autograd: worst {worst} {errs[worst]:.2e}, "
+          f"median {sorted(errs.values())[len(errs) // 2]:.2e}; loss {float(loss):.6f} vs {float(l64):.6f}")
+    assert errs[worst] <= 5e-4
+
+
+@pytest.mark.gpu
+def test_training_steps_reduce_the_loss():
+    """utils/train.py:149-158 in miniature: Adam + gradient clipping on the MSE of the predicted positions."""
+    w = synth.WORKLOADS["water3d_10k"]
+    host = synth.make_partitions(w, n_nodes=5000, seed=41)[0]
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 4, seed=3, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=4), sd).train()
+    inp = to_dev(host)
+    target = inp["node_loc"] + 0.01 * inp["node_vel"] + 0.002
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        out, X = m(**inp)
+        loss = torch.nn.functional.mse_loss(out, target)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 0.3)
+        opt.step()
+        losses.append(float(loss))
+    print("training losses", [f"{l:.3e}" for l in losses])
+    assert losses[-1] < 0.7 * losses[0]
