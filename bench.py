@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample-nodes", type=int, default=50_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary forward+backward measurement")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the forward as a CUDA graph in the timed region (single GPU only; auto = off)")
     return ap.parse_args()
@@ -361,6 +362,38 @@ def run_ours(args, w, rank, world, local_rank):
                    "wall_ms_per_step": max_over_ranks(t_e2e_wall) * 1e3,
                    "includes": "H2D of all inputs from pinned host memory, CSR build, forward, D2H of outputs"}
 
+    # ---- secondary: train step = forward + backward through the fused kernels ----
+    train = None
+    if not args.no_train:
+        model.train()
+        target = (inp["node_loc"] + 0.01 * inp["node_vel"]).detach()
+        for p_ in model.parameters():
+            p_.grad = None
+
+        def train_step():
+            o, xv = model(**inp)
+            loss = torch.nn.functional.mse_loss(o, target) + 1e-3 * xv.square().mean()
+            loss.backward()
+
+        train_step()
+        barrier()
+        n_tr = max(2, min(args.steps, 3))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n_tr):
+            train_step()
+        e.record()
+        barrier()
+        t_tr = max_over_ranks(s.elapsed_time(e) * 1e-3 / n_tr)
+        train = {"value": 1.0 / t_tr, "unit": "train-steps/s", "ms_per_step": t_tr * 1e3, "steps": n_tr,
+                 "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+                 "includes": "forward (sm_100a kernels, activations kept per layer) + backward (hand-written edge and "
+                             "real<->virtual backward kernels, dense per-node stages via torch recompute, packed "
+                             "gradient all-reduce); no optimizer step"}
+        model.eval()
+        for p_ in model.parameters():
+            p_.grad = None
+
     t_step = max_over_ranks(t_dev / args.steps)
     e_total = int(sum_over_ranks(E))
     n_total = int(sum_over_ranks(N))
@@ -396,8 +429,9 @@ def run_ours(args, w, rank, world, local_rank):
                 "graph_gen_s": round(t_gen, 2), "first_forward_s": round(t_first, 3)},
             "clocks": clocks,
             "e2e": e2e,
+            "train_step": train,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "edge_layer_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "edge_layer_cs_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "bytes_per_launch": bytes_edge, "ms_per_launch": t_edge * 1e3, "peak_source": peak_src,
                          "note": "rank-0 kernel; algorithmic bytes = E*284 + N*536 (SURVEY §8d)"},

@@ -15,9 +15,12 @@ DistEGNN forward over graph partitions.
 
 What it does NOT do: the reference's datasets are not redistributable and its data pipeline needs PyG/h5py/
 MDAnalysis, so inputs are the seeded synthetic restatement of the configured dataset (`distegnn_b200/synth.py`:
-same node/edge statistics, `radius`/`split_mode` semantics of datasets/distribute_graphs.py); and this release is
-forward-only, so instead of the training loop (utils/train.py) it evaluates `--eval_steps` forward passes and
-reports graph-steps/s, edges/s and the MSE against a zero-displacement target.  Training = scope row f-1.
+same node/edge statistics, `radius`/`split_mode` semantics of datasets/distribute_graphs.py) with a synthetic
+target (constant-velocity step).  It evaluates `--eval_steps` forward passes (graph-steps/s, edges/s) and, with
+`--train_steps K`, runs K optimisation steps of the reference's training step (utils/train.py:98-158: node-count
+weighted MSE x world_size, MMD regulariser on the virtual coordinates, gradient clipping 0.3, Adam) through the
+fused forward AND backward kernels under DDP — the epoch loop, loaders, checkpoints and wandb logging of
+utils/train.py stay with the reference (out of scope).
 """
 from __future__ import annotations
 
@@ -74,6 +77,8 @@ def parse():
     p.add_argument("--virtual_channels", type=int, default=None)
     p.add_argument("--eval_steps", type=int, default=10, help="(new) forward passes to time")
     p.add_argument("--nodes", type=int, default=None, help="(new) override the synthetic node count")
+    p.add_argument("--train_steps", type=int, default=0, help="(new) optimisation steps of the reference's training "
+                   "step (utils/train.py:98-158) on the synthetic target")
     return p.parse_args()
 
 
@@ -167,8 +172,57 @@ def main():
               f"edges(sum over partitions)={int(cnt[1])}  forward {dt * 1e3:.3f} ms  "
               f"{1.0 / dt:.2f} graph-steps/s  {cnt[1].item() / dt / 1e6:.1f} M edges/s  "
               f"mean squared displacement {se.item() / (3 * cnt[0].item()):.4e}  virtual_loc {tuple(X.shape)}")
+    if args.train_steps > 0:
+        train_steps(args, cfg, model, inp, forward, world_size, local_rank, distributed)
     if distributed:
         dist.destroy_process_group()
+
+
+def train_steps(args, cfg, model, inp, forward, world_size, local_rank, distributed):
+    """utils/train.py:98-158 on one (partitioned) synthetic graph: loss = n_r/Σn · MSE_r · world_size (DDP averages the
+    gradients, the reference wants their sum) + MMD between the virtual coordinates and sampled target positions."""
+    tc = cfg.get("train", {}) or {}
+    mmd = tc.get("mmd", {}) or {}
+    sigma, mmd_w, samples = float(mmd.get("sigma", 3)), float(mmd.get("weight", 0.01)), int(mmd.get("samples", 50))
+    lr = args.lr if args.lr is not None else float(tc.get("lr", 5e-4))
+    C = cfg["model"]["virtual_channels"]
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=float(tc.get("weight_decay", 1e-12)))
+    target = inp["node_loc"] + 0.01 * inp["node_vel"]          # synthetic: one constant-velocity step
+    n_r = torch.tensor(float(target.shape[0]), device=local_rank)
+    n_tot = n_r.clone()
+    if distributed:
+        dist.all_reduce(n_tot)
+
+    def kernel(x, y):                                          # utils/train.py:11-14
+        return torch.exp(-torch.cdist(x, y, p=2) / (2 * sigma * sigma))
+
+    t_step = []
+    for step in range(args.train_steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loc_pred, X = forward()
+        mse = torch.nn.functional.mse_loss(loc_pred, target)
+        loss = n_r / n_tot * mse
+        logged = loss.detach().clone()
+        if distributed:
+            dist.all_reduce(logged)
+        loss = world_size * loss
+        Xv = X.permute(0, 2, 1)[0]                              # [C,3] (batch_size 1)
+        idx = torch.randperm(target.shape[0], device=target.device)[:samples * C]
+        l_vv = kernel(Xv, Xv).sum() / C / C
+        l_rv = 2 * kernel(target[idx], Xv).sum() / (samples * C) / C
+        loss = loss + mmd_w * world_size * n_r / n_tot * (l_vv - l_rv)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=0.3)
+        opt.step()
+        torch.cuda.synchronize()
+        t_step.append(time.perf_counter() - t0)
+        if local_rank == 0:
+            print(f"train step {step}: MSE {logged.item():.6e}  ({t_step[-1] * 1e3:.1f} ms)")
+    if local_rank == 0 and len(t_step) > 2:
+        print(f"train step time (median of {len(t_step)}): {sorted(t_step)[len(t_step) // 2] * 1e3:.2f} ms")
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/gpu_tests_$TAG.l
 tail -3 gpurun_out/gpu_tests_$TAG.log
 for lib in default distegnn_b200/variants/*.so; do
   if [ $lib = default ]; then unset DISTEGNN_B200_LIB; else export DISTEGNN_B200_LIB=$GRAFT_REPO_ROOT/$lib; fi
-  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('VARIANT $lib', round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['kernel_ms'].items()})"
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-train 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('VARIANT $lib', round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['kernel_ms'].items()})"
 done
 unset DISTEGNN_B200_LIB
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"edge_layer_cs|edge_layer_t16|virtual_layer_t16" -s 2 -c 2 -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/b_ncu_$TAG.log 2>&1; echo ncu rc=$?
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"edge_layer_cs|edge_layer_t16|virtual_layer_t16" -s 2 -c 2 -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-train > gpurun_out/b_ncu_$TAG.log 2>&1; echo ncu rc=$?
