@@ -357,7 +357,45 @@ def run_ours(args, w, rank, world, local_rank):
             t_e2e_wall = (time.perf_counter() - w0) / n_e2e
             t_e2e = max(s.elapsed_time(e) * 1e-3 / n_e2e, 0.0)
             t_e2e = max_over_ranks(max(t_e2e, 0.0))
+            # same bytes every step, but the H2D of step i+1 is issued on a copy stream while step i computes (what a
+            # prefetching loader with pinned memory does); reported NEXT TO the serialised number, never instead of it
+            copy_stream = torch.cuda.Stream(device=dev)
+
+            def prefetch():
+                with torch.cuda.stream(copy_stream):
+                    d = {k: (v.to(dev, non_blocking=True) if v is not None else None) for k, v in pinned.items()}
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                return d, ev
+
+            def consume(d, ev):
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(ev)
+                for v in d.values():
+                    if v is not None:
+                        v.record_stream(cur)
+                o, xv = model(**d)
+                out_host.copy_(o, non_blocking=True)
+                X_host.copy_(xv, non_blocking=True)
+
+            nxt = prefetch()
+            consume(*nxt)
+            barrier()
+            nxt = prefetch()
+            s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s2.record()
+            for i in range(n_e2e):
+                cur_in = nxt
+                if i + 1 < n_e2e:
+                    nxt = prefetch()
+                consume(*cur_in)
+            e2.record()
+            barrier()
+            t_pipe = max_over_ranks(s2.elapsed_time(e2) * 1e-3 / n_e2e)
             e2e = {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+                   "pipelined": {"value": 1.0 / t_pipe, "ms_per_step": t_pipe * 1e3,
+                                 "note": "same per-step copies, H2D of step i+1 overlapped with the forward of step i "
+                                         "on a copy stream (the first H2D of the timed region is not hidden)"},
                    "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": t_e2e * 1e3,
                    "wall_ms_per_step": max_over_ranks(t_e2e_wall) * 1e3,
                    "includes": "H2D of all inputs from pinned host memory, CSR build, forward, D2H of outputs"}
