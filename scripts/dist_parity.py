@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--workload", default="fluid113k")
     ap.add_argument("--nodes", type=int, default=None)
     ap.add_argument("--split-mode", default="random")
+    ap.add_argument("--grads", action="store_true", help="also check the training path: parameter gradients of "
+                    "sum_r <out_r, cot_r> + <X, cot_X>, summed over the ranks, against float64 autograd through the "
+                    "partitioned oracle (use a small --nodes: the oracle runs on the host)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -72,6 +75,39 @@ def main():
             ok &= err <= 1e-5 * max(1.0, float(refs[r].abs().max())) and err / disp <= 1e-4 and ex <= 1e-5 and same
         print("DIST_PARITY", "PASS" if ok else "FAIL", f"world={world} split={args.split_mode} {args.workload}",
               flush=True)
+    if args.grads:
+        g = torch.Generator().manual_seed(17)
+        cots = [torch.randn(n, 3, generator=g) for n in sizes]
+        cotX = torch.randn(X.shape, generator=g)
+        m.train()
+        out, X = m(**inp)
+        ((out * cots[rank].to(dev)).sum() + (X * cotX.to(dev)).sum()).backward()
+        names = [k for k, _ in m.named_parameters()]
+        flat = torch.cat([(p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1) for _, p_ in m.named_parameters()])
+        dist.all_reduce(flat)                                    # Σ over ranks of each rank's parameter gradient
+        if rank == 0:
+            sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+            p64 = [{k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in p.items()}
+                   for p in parts]
+            refs, refX = orc.forward_partitions(sd64, [{k: v for k, v in p.items() if k != "loc_mean"} for p in p64],
+                                                p64[0]["loc_mean"], normalize=w.normalize)
+            loss = sum((refs[r] * cots[r].double()).sum() for r in range(world)) + world * (refX * cotX.double()).sum()
+            rg = torch.autograd.grad(loss, [sd64[k] for k in names], allow_unused=True)
+            off, worst, wk = 0, 0.0, ""
+            for k, r_ in zip(names, rg):
+                n = sd[k].numel()
+                mine = flat[off:off + n].cpu().double().reshape(sd[k].shape)
+                off += n
+                if r_ is None or float(r_.abs().max()) == 0.0:
+                    ok &= float(mine.abs().max()) == 0.0
+                    continue
+                e = float((mine - r_).abs().max() / r_.abs().max())
+                if e > worst:
+                    worst, wk = e, k
+            print(f"gradients summed over {world} ranks vs float64 autograd through the partitioned oracle: worst "
+                  f"{wk} {worst:.3e}", flush=True)
+            ok &= worst <= 5e-4
+            print("DIST_GRAD_PARITY", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
