@@ -35,7 +35,7 @@ SIGNATURES = {
     "distegnn_embed_fwd": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
     "distegnn_embed_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
     "distegnn_edge_layer_fwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 15,
+    "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
     "distegnn_virtual_layer_bwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
     "distegnn_edge_layer_fwd_t16": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_edge_layer_fwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,

@@ -83,12 +83,11 @@ class CudaBackend:
                                                self._s(x4)), "edge_layer_fwd")
         self.launches += 1 if E else 0
 
-    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, wT, g_agg_m, g_agg_x, g_P, g_Q, g_x4,
-                       g_lp) -> None:
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
         """Backward of edge_layer: accumulates into g_P, g_Q, g_x4 and the parameter-gradient block g_lp."""
         N, E, A, Cn, Na = dims
         check(self.lib.distegnn_edge_layer_bwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea), ptr(x4), ptr(P),
-                                               ptr(Q), ptr(lp), ptr(wT), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P), ptr(g_Q),
+                                               ptr(Q), ptr(lp), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P), ptr(g_Q),
                                                ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd")
         self.launches += 1 if E else 0
 

@@ -534,9 +534,8 @@ class _FastEGNNFunction(torch.autograd.Function):
                                  g_agg_v, g_trans_v, g_vsum, g_Hn_i, g_xv, g_G_i, g_Xv_acc, g_lps[i])
             # ---- 4. per-edge stage (CUDA) --------------------------------------------------------------------------------
             g_P_i, g_Q_i, g_x4e = zeros(N, H), zeros(N, H), zeros(N, 4)
-            wTe = torch.stack([lp[offs[k]:offs[k] + H * H].view(H, H).t().contiguous() for k in ("E_W2", "E_WC")])
             be.edge_layer_bwd((N, E, A, Cn, Na), S["flags"], a["row"], a["col"], a["ea"], S["x4"], S["P"], S["Q"], lp,
-                              wTe, g_agg_m, g_agg_x, g_P_i, g_Q_i, g_x4e, g_lps[i])
+                              g_agg_m, g_agg_x, g_P_i, g_Q_i, g_x4e, g_lps[i])
             g_x = g_x_i + g_xv[:, :3] + g_x4e[:, :3]
             g_h, g_P, g_Q, g_Hn = g_h_i, g_P_i, g_Q_i, g_Hn_i
             g_Xv, g_Hv, g_G = g_Xv_acc, g_Hv_i, g_G_i

@@ -169,16 +169,15 @@ DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A
 
 /* Backward of distegnn_edge_layer_fwd (in the reference: autograd through models/FastEGNN.py:144-150,
  * 169-177, 206, 237-246, 322-337).  Nothing of size [E,.] is kept from the forward pass: every 128-edge tile is
- * recomputed.  Inputs: the forward inputs, wT = the matrices E_W2, E_WC of the parameter block TRANSPOSED ([2][64][64],
- * wT[m][n*64+k] = W_m[k*64+n]), plus g_agg_m [N,64] (gradient w.r.t. the SUM agg_m; may be NULL with
+ * recomputed.  Inputs: the forward inputs plus g_agg_m [N,64] (gradient w.r.t. the SUM agg_m; may be NULL with
  * FLAG_LAST) and g_agg_x [N,4] (w.r.t. the SUM agg_x).  Outputs are ACCUMULATED (+=): g_P, g_Q [N,64], g_x4 [N,4]
  * (both edge endpoints; the normalisation norm is detached as in :243) and g_layer_params, a buffer with the layout
  * of the parameter block (fields E_W1R, E_W1E, E_W2, E_B2, E_WC, E_BC, E_W3 are written). */
 DISTEGNN_API int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                          const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                          const float* x4, const float* P, const float* Q, const float* layer_params,
-                                         const float* wT, const float* g_agg_m, const float* g_agg_x, float* g_P,
-                                         float* g_Q, float* g_x4, float* g_layer_params, void* stream);
+                                         const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
+                                         float* g_x4, float* g_layer_params, void* stream);
 
 /* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
  * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile.  Inputs: the forward inputs, wT = the three

@@ -146,7 +146,7 @@ class ShadowBackend:
 
     # ---- backward stand-ins (torch.autograd over tests/shadow_autograd.py): same accumulate / write contracts as
     # distegnn_edge_layer_bwd / distegnn_virtual_layer_bwd, so that FastEGNN's training path can run on CPU ---------
-    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, wT, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp):
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp):
         from tests import shadow_autograd as sa
         N, E, A, C, Na = dims
         if E == 0:

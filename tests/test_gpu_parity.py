@@ -647,10 +647,7 @@ def test_edge_stage_backward(flags, A):
     rP, rQ, rx, rlp = torch.autograd.grad(loss, (Pd, Qd, xd, lpd))
     # kernel
     gP, gQ, gx4, glp = (torch.zeros_like(t) for t in (P, Q, x4, lp))
-    offs, _ = _lib.param_layout(A, C, Na)
-    wT = torch.stack([lp[offs[k]:offs[k] + 4096].view(64, 64).t().contiguous() for k in ("E_W2", "E_WC")])
-    be.edge_layer_bwd((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, lp, wT, None if last else g_m, g_x, gP, gQ, gx4,
-                      glp)
+    be.edge_layer_bwd((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, lp, None if last else g_m, g_x, gP, gQ, gx4, glp)
     torch.cuda.synchronize()
     errs = dict(P=_rel(gP, rP), Q=_rel(gQ, rQ), x=_rel(gx4[:, :3], rx), params=_rel(glp, rlp))
     offs, _ = _lib.param_layout(A, C, Na)
