@@ -192,6 +192,24 @@ DISTEGNN_API int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A
                                             float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
                                             void* stream);
 
+/* On-device radius graph: replaces the host-side `radius_graph(pos_i, r=radius, max_num_neighbors=N)`
+ * + `edge_attr = |dx|` of the reference's partitioners (datasets/distribute_graphs.py:43-44; PyG / torch_cluster).
+ * Uniform-grid cell list; the caller sorts the nodes' cell keys (key = graph*ncell + (ix*ny + iy)*nz + iz, cell size >=
+ * radius, ix = (int)((x - origin_x) * (1/cell)) clamped to the grid) and passes `order` (node ids in key order) and the
+ * dense table cell_start[n_graphs*ncell + 1] (first position of every key).  origin_host[3] / dims_host[3] are HOST
+ * arrays.  Two phases because the edge count is only known after the first:
+ *   distegnn_radius_count -> deg[i] = number of j (same graph, j != i unless loop) with |x_i - x_j| <= radius
+ *   caller: rowptr = exclusive prefix sum of deg (int64 [N+1]), allocates E = rowptr[N] entries
+ *   distegnn_radius_fill  -> row[e] = i, col[e] = j for e in [rowptr[i], rowptr[i+1]), dist[e] = |x_i - x_j| (dist may be
+ *                            NULL): edges grouped by destination row, rows ascending. */
+DISTEGNN_API int distegnn_radius_count(int64_t n_nodes, const float* x4, const int32_t* batch32, const int32_t* order,
+                                       const int64_t* cell_start, const float* origin_host, float cell_size,
+                                       const int32_t* dims_host, float radius, int loop, int32_t* deg, void* stream);
+DISTEGNN_API int distegnn_radius_fill(int64_t n_nodes, const float* x4, const int32_t* batch32, const int32_t* order,
+                                      const int64_t* cell_start, const float* origin_host, float cell_size,
+                                      const int32_t* dims_host, float radius, int loop, const int64_t* rowptr,
+                                      int32_t* row, int32_t* col, float* dist, void* stream);
+
 /* Same contract as distegnn_edge_layer_fwd: the thread-per-row tcgen05 kernel (16 warps per SM, 128 registers per
  * thread; csrc/edge_layer_tc16.cu).  The production symbol runs the column-split flavour (two threads per row, 32
  * warps per SM; csrc/edge_layer_cs.cu); this twin is kept for cross-checks and A/B timing. */

@@ -792,3 +792,60 @@ def test_training_steps_reduce_the_loss():
         losses.append(float(loss))
     print("training losses", [f"{l:.3e}" for l in losses])
     assert losses[-1] < 0.7 * losses[0]
+
+
+# ---- on-device graph construction against scipy's cKDTree (the synthetic-data generator's own builder) ----
+def _edge_set(ei):
+    ei = ei.cpu().numpy()
+    return set(zip(ei[0].tolist(), ei[1].tolist()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,r,B,loop", [(20_000, 0.075, 1, False), (3_000, 0.2, 7, False), (500, 0.5, 3, True),
+                                        (1, 0.1, 1, False)])
+def test_radius_graph_matches_kdtree(n, r, B, loop):
+    from scipy.spatial import cKDTree
+    from distegnn_b200 import radius_graph
+    rng = np.random.default_rng(5)
+    side = synth.box_side(n, r, 15.0) if B == 1 else 2.0
+    pos = rng.uniform(0, side, size=(n, 3)).astype(np.float32)
+    batch = np.sort(rng.integers(0, B, size=n)).astype(np.int64)
+    ref = set()
+    for g in range(B):
+        ids = np.nonzero(batch == g)[0]
+        if len(ids) == 0:
+            continue
+        pairs = cKDTree(pos[ids].astype(np.float64)).query_pairs(r, output_type="ndarray")
+        for i, j in pairs:
+            ref.add((int(ids[i]), int(ids[j])))
+            ref.add((int(ids[j]), int(ids[i])))
+        if loop:
+            ref.update((int(i), int(i)) for i in ids)
+    ei, ea = radius_graph(torch.from_numpy(pos).to(dev()), r, None if B == 1 else torch.from_numpy(batch).to(dev()),
+                          loop=loop, max_num_neighbors=n)
+    mine = _edge_set(ei)
+    # pairs whose length is within one fp32 ulp of r may fall on either side (cKDTree works in float64)
+    d = np.linalg.norm(pos[ei[0].cpu().numpy()].astype(np.float64) - pos[ei[1].cpu().numpy()].astype(np.float64), axis=1)
+    border = {e for e in (mine ^ ref) if abs(np.linalg.norm(pos[e[0]].astype(np.float64) - pos[e[1]].astype(np.float64)) - r) < 1e-6}
+    assert (mine ^ ref) == border, (len(mine), len(ref), len(mine ^ ref))
+    assert ei.shape[1] == len(mine)                                   # no duplicates
+    assert bool((ei[0][1:] >= ei[0][:-1]).all())                      # grouped by destination row, ascending
+    assert ea.shape == (ei.shape[1], 2) and float((ea[:, 0].cpu().double() - torch.from_numpy(d)).abs().max() if len(d) else 0.0) <= 1e-6
+    print(f"radius_graph n={n} r={r} B={B} loop={loop}: {ei.shape[1]} edges, {len(border)} border pairs")
+
+
+@pytest.mark.gpu
+def test_radius_graph_feeds_the_model_like_the_host_built_graph():
+    """Same model output whether the graph comes from the host builder (cKDTree) or from the device builder."""
+    from distegnn_b200 import radius_graph
+    w = synth.WORKLOADS["water3d_10k"]
+    host = synth.make_partitions(w, n_nodes=8000, seed=3)[0]
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 2, seed=4, coord_gain=0.05)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=2), sd)
+    inp = to_dev(host)
+    with torch.no_grad():
+        out_h, X_h = m(**inp)
+        ei, ea = radius_graph(inp["node_loc"], w.radius)
+        assert ei.shape[1] == inp["edge_index"].shape[1]
+        out_d, X_d = m(**{**inp, "edge_index": ei, "edge_attr": ea})
+    assert max_abs(out_h, out_d) <= 2e-6 and max_abs(X_h, X_d) <= 2e-6
