@@ -152,6 +152,13 @@ class CudaBackend:
                                                     ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
                                                     ptr(agg_x), self._s(x4)), "edge_layer_fwd_tf32")
 
+    def virtual_layer_cs(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
+        """thread-per-row tcgen05 twin of virtual_layer (cross-check / A-B timing only)."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_layer_fwd_cs(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
+                                                      ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
+                                                      ptr(vsum), self._s(x4)), "virtual_layer_fwd_cs")
+
     def virtual_layer_tf32(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
         """3xTF32 tensor-core twin of virtual_layer (cross-check / A-B timing only)."""
         N, B, A, Cn, Na = dims

@@ -1,4 +1,5 @@
-// Real<->virtual stage on the tensor cores — production kernel behind distegnn_virtual_layer_fwd.
+// Real<->virtual stage on the tensor cores — production kernel behind distegnn_virtual_layer_fwd (thread per row; the
+// column-split flavour virtual_layer_cs.cu, exported as distegnn_virtual_layer_fwd_cs, measured 2 % slower: kept as a twin).
 // Replaces reference models/FastEGNN.py:252-253 (virtual geometry), 154-163 (edge_mode_virtual), 180, 191-193,
 // 207, 220-223 (virtual halves of coord_model_vel / coord_model_virtual / node_model / node_model_virtual) and
 // the global_mean_pool scatters at :193,:222.  Same math/outputs as virtual_layer.cu (fp32-FMA twin) and

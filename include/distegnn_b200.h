@@ -179,6 +179,13 @@ DISTEGNN_API int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A
                                          const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
                                          float* g_x4, float* g_layer_params, void* stream);
 
+/* Same contract as distegnn_virtual_layer_fwd: the column-split flavour (two threads per row, 32 warps per SM;
+ * csrc/virtual_layer_cs.cu) — measured 2 % slower than the production thread-per-row kernel; kept as a twin. */
+DISTEGNN_API int distegnn_virtual_layer_fwd_cs(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                                                const int32_t* batch32, const float* x4, const float* Hn,
+                                                const float* Xv, const float* G, const float* layer_params,
+                                                float* agg_v, float* trans_v, float* vsum, void* stream);
+
 /* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
  * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile.  Inputs: the forward inputs, wT = the three
  * 64x64 matrices V_W2, V_WXV, V_WX of the parameter block TRANSPOSED ([3][64][64], wT[m][n*64+k] = W_m[k*64+n]), and the

@@ -209,7 +209,7 @@ def test_edge_kernel_silu_batch_guard():
         assert e_m <= 5e-6 and e_x <= 5e-5
 
 
-@pytest.mark.parametrize("C,B", [(8, 1), (5, 1), (3, 7)])
+@pytest.mark.parametrize("C,B", [(8, 1), (5, 1), (3, 7), (1, 2), (16, 3)])
 def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
     """tcgen05 virtual-stage kernel against its fp32-FMA twin (single graph and a batch whose tiles
     straddle graph boundaries; C = 8 / 5 / 3 exercise full and ragged row tiles)."""
@@ -230,13 +230,14 @@ def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
     K = 4 + 3 * C + 64 * C
     for flags in (0, _lib.FLAG_LAST):
         outs = []
-        for fn in (be.virtual_layer_simt, be.virtual_layer, be.virtual_layer_tf32):
+        for fn in (be.virtual_layer_simt, be.virtual_layer, be.virtual_layer_tf32, be.virtual_layer_cs):
             agg_v, trans_v = torch.zeros(N, 64, device=d), torch.zeros(N, 4, device=d)
             vsum = torch.zeros(B, K, device=d)
             fn((N, B, 2, C, 0), flags, batch, x4, Hn, Xv, G, lp, None if flags else agg_v, trans_v, vsum)
             torch.cuda.synchronize()
             outs.append((agg_v, trans_v[:, :3], vsum))
-        for impl, o in (("fp16-split", outs[1]), ("3xTF32", outs[2])):
+        for impl, o in (("fp16-split thread-per-row (production)", outs[1]), ("3xTF32", outs[2]),
+                        ("fp16-split column-split", outs[3])):
             for name, x, y in zip(("agg_v", "trans_v", "vsum"), o, outs[0]):
                 err = max_abs(x, y) / max(1e-9, float(y.abs().max()))
                 print(f"C={C} B={B} flags={flags} {impl} {name}: rel err {err:.3e}")
