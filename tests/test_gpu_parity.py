@@ -850,3 +850,35 @@ def test_radius_graph_feeds_the_model_like_the_host_built_graph():
         assert ei.shape[1] == inp["edge_index"].shape[1]
         out_d, X_d = m(**{**inp, "edge_index": ei, "edge_attr": ea})
     assert max_abs(out_h, out_d) <= 2e-6 and max_abs(X_h, X_d) <= 2e-6
+
+
+@pytest.mark.gpu
+def test_training_path_gradients_batched_nbody():
+    """BASELINE config 1 shape (N-body, fully connected, normalize=True) as a batch of graphs: tiles straddle graph
+    boundaries in every kernel, forward and backward; gradients against float64 autograd through the oracle."""
+    w = synth.WORKLOADS["nbody100"]
+    nb, n = 12, 100
+    parts = [synth.make_partitions(w, seed=50 + s)[0] for s in range(nb)]
+    cat = lambda k: torch.cat([p[k] for p in parts])
+    inp = dict(node_feat=cat("node_feat"), node_loc=cat("node_loc"), node_vel=cat("node_vel"), loc_mean=cat("loc_mean"),
+               edge_index=torch.cat([p["edge_index"] + i * n for i, p in enumerate(parts)], 1),
+               data_batch=torch.arange(nb).repeat_interleave(n), edge_attr=cat("edge_attr"), node_attr=None)
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 4, seed=19, coord_gain=0.05)
+    kw = dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=4, normalize=True)
+    g = torch.Generator().manual_seed(23)
+    cot_out, cot_X = torch.randn(nb * n, 3, generator=g), torch.randn(nb, 3, 3, generator=g)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    inp64 = {k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in inp.items()}
+    o64, X64 = orc.forward(sd64, **inp64, normalize=True)
+    keys = list(sd64)
+    ref = dict(zip(keys, torch.autograd.grad((o64 * cot_out.double()).sum() + (X64 * cot_X.double()).sum(),
+                                             [sd64[k] for k in keys], allow_unused=True)))
+    ref = {k: (v if v is not None else torch.zeros_like(sd64[k])) for k, v in ref.items()}
+    m = cuda_model(kw, sd).train()
+    out, X = m(**to_dev(inp))
+    ((out * cot_out.to(dev())).sum() + (X * cot_X.to(dev())).sum()).backward()
+    errs, dead = _param_grad_errors(m, ref)
+    worst = max(errs, key=errs.get)
+    print(f"nbody batch {nb}x{n}: gradients vs oracle fp64 autograd: worst {worst} {errs[worst]:.2e}, "
+          f"median {sorted(errs.values())[len(errs) // 2]:.2e}")
+    assert errs[worst] <= 5e-4
