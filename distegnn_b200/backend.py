@@ -124,6 +124,13 @@ class CudaBackend:
                                             ptr(rowptr), ptr(row), ptr(col), ptr(dist), self._s(x4)), "radius_fill")
         self.launches += 1 if N else 0
 
+    def edge_layer_bwd_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
+        """fp32-FMA twin of edge_layer_bwd (cross-check only)."""
+        N, E, A, Cn, Na = dims
+        check(self.lib.distegnn_edge_layer_bwd_simt(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea), ptr(x4),
+                                                    ptr(P), ptr(Q), ptr(lp), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P),
+                                                    ptr(g_Q), ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd_simt")
+
     def edge_layer_t16(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
         """thread-per-row tcgen05 twin of edge_layer (cross-check / A-B timing only)."""
         N, E, A, Cn, Na = dims

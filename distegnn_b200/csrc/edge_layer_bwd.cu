@@ -1,4 +1,5 @@
-// Backward of the real<->real edge stage — fp32 FMA on the CUDA cores, correctness first.
+// Backward of the real<->real edge stage — fp32 FMA on the CUDA cores: the first, correctness-first
+// kernel, now behind distegnn_edge_layer_bwd_simt as the twin of the tensor-core kernel (edge_layer_bwd_tc.cu).
 // Differentiates what distegnn_edge_layer_fwd computes (reference models/FastEGNN.py:237-246 coord2radial,
 // :144-150 edge_model, :169-177 edge part of coord_model_vel, :206 edge part of node_model, scatter_add_ :322-337;
 // in the reference this is autograd through ~20 [E,64] tensors):
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_layer_bwd_kernel(const EdgeB
 
 }  // namespace degnn
 
-extern "C" int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+extern "C" int distegnn_edge_layer_bwd_simt(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q, const float* layer_params,
                                        const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q, float* g_x4,

@@ -217,6 +217,14 @@ DISTEGNN_API int distegnn_radius_fill(int64_t n_nodes, const float* x4, const in
                                       const int32_t* dims_host, float radius, int loop, const int64_t* rowptr,
                                       int32_t* row, int32_t* col, float* dist, void* stream);
 
+/* Same contract as distegnn_edge_layer_bwd, every tile GEMM as fp32 FMA on the CUDA cores (csrc/edge_layer_bwd.cu): the
+ * first backward kernel, kept as the twin of the tensor-core one for cross-checks. */
+DISTEGNN_API int distegnn_edge_layer_bwd_simt(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
+                                              const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
+                                              const float* x4, const float* P, const float* Q, const float* layer_params,
+                                              const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
+                                              float* g_x4, float* g_layer_params, void* stream);
+
 /* Same contract as distegnn_edge_layer_fwd: the thread-per-row tcgen05 kernel (16 warps per SM, 128 registers per
  * thread; csrc/edge_layer_tc16.cu).  The production symbol runs the column-split flavour (two threads per row, 32
  * warps per SM; csrc/edge_layer_cs.cu); this twin is kept for cross-checks and A/B timing. */

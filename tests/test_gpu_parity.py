@@ -646,18 +646,20 @@ def test_edge_stage_backward(flags, A):
     am, ax = sa.edge_stage((N, E, A, C, Na), flags, row, col, ea.double() if A else None, xd, Pd, Qd, lpd)
     loss = (ax * g_x[:, :3].double()).sum() + (0 if last else (am * g_m.double()).sum())
     rP, rQ, rx, rlp = torch.autograd.grad(loss, (Pd, Qd, xd, lpd))
-    # kernel
-    gP, gQ, gx4, glp = (torch.zeros_like(t) for t in (P, Q, x4, lp))
-    be.edge_layer_bwd((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, lp, None if last else g_m, g_x, gP, gQ, gx4, glp)
-    torch.cuda.synchronize()
-    errs = dict(P=_rel(gP, rP), Q=_rel(gQ, rQ), x=_rel(gx4[:, :3], rx), params=_rel(glp, rlp))
+    # kernels: the tensor-core production kernel and its fp32-FMA twin
     offs, _ = _lib.param_layout(A, C, Na)
-    for k in ("E_W1R", "E_W1E", "E_W2", "E_B2", "E_WC", "E_BC", "E_W3"):
-        n = {"E_W1E": A * 64, "E_W2": 4096, "E_WC": 4096}.get(k, 64)
-        if n:
-            errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
-    print(f"edge stage backward flags={flags} A={A}: rel err vs float64 autograd {errs}")
-    assert max(errs.values()) <= 2e-5
+    for name, fn in (("tcgen05", be.edge_layer_bwd), ("fp32-FMA twin", be.edge_layer_bwd_simt)):
+        gP, gQ, gx4, glp = (torch.zeros_like(t) for t in (P, Q, x4, lp))
+        fn((N, E, A, C, Na), flags, row, col, ea, x4, P, Q, lp, None if last else g_m, g_x, gP, gQ, gx4, glp)
+        torch.cuda.synchronize()
+        errs = dict(P=_rel(gP, rP), Q=_rel(gQ, rQ), x=_rel(gx4[:, :3], rx), params=_rel(glp, rlp))
+        for k in ("E_W1R", "E_W1E", "E_W2", "E_B2", "E_WC", "E_BC", "E_W3"):
+            n = {"E_W1E": A * 64, "E_W2": 4096, "E_WC": 4096}.get(k, 64)
+            if n:
+                errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
+        print(f"edge stage backward [{name}] flags={flags} A={A}: rel err vs float64 autograd "
+              + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+        assert max(errs.values()) <= 2e-5, name
 
 
 @pytest.mark.gpu
