@@ -38,6 +38,8 @@ SIGNATURES = {
     "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
     "distegnn_edge_layer_bwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
     "distegnn_virtual_layer_bwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
+    "distegnn_virtual_layer_bwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
+    "distegnn_virtual_bwd_prepare": [_i32, _i32, _i32, _vp, _vp, _vp],
     "distegnn_radius_count": [_i64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, _i32, _vp, _vp],
     "distegnn_radius_fill": [_i64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, _i32, _vp, _vp, _vp, _vp, _vp],
     "distegnn_edge_layer_fwd_t16": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,

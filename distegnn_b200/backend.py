@@ -91,38 +91,33 @@ class CudaBackend:
                                                ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd")
         self.launches += 1 if E else 0
 
-    def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
+    def virtual_bwd_prepare(self, A, Cn, Na, lp) -> "torch.Tensor":
+        """fp16 hi/lo operand images of the virtual stage's weights and their transposes (96 KB) for virtual_layer_bwd."""
+        import torch
+        img = torch.empty(6 * 2 * 64 * 64, dtype=torch.float16, device=lp.device)
+        check(self.lib.distegnn_virtual_bwd_prepare(A, Cn, Na, ptr(lp), ptr(img), self._s(lp)), "virtual_bwd_prepare")
+        self.launches += 1
+        return img
+
+    def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wimg, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
                           g_G, g_Xv, g_lp) -> None:
-        """Backward of virtual_layer: writes g_Hn, g_xv; accumulates into g_G, g_Xv and the parameter-gradient block."""
+        """Backward of virtual_layer (tcgen05): writes g_Hn, g_xv; accumulates into g_G, g_Xv and the parameter gradients.
+        `wimg` comes from virtual_bwd_prepare(lp)."""
         N, B, A, Cn, Na = dims
         check(self.lib.distegnn_virtual_layer_bwd(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn), ptr(Xv),
-                                                  ptr(G), ptr(lp), ptr(wT), ptr(g_agg_v), ptr(g_trans_v), ptr(g_vsum),
+                                                  ptr(G), ptr(lp), ptr(wimg), ptr(g_agg_v), ptr(g_trans_v), ptr(g_vsum),
                                                   ptr(g_Hn), ptr(g_xv), ptr(g_G), ptr(g_Xv), ptr(g_lp), self._s(x4)),
               "virtual_layer_bwd")
         self.launches += 1 if N else 0
 
-    @staticmethod
-    def _grid_host(grid):
-        import ctypes as C
-        origin, cell, dims = grid
-        return (C.c_float * 3)(*origin), float(cell), (C.c_int32 * 3)(*dims)
-
-    def radius_count(self, N, x4, batch32, order32, cell_start, grid, r, loop, deg) -> None:
-        """Neighbour counts of the on-device radius graph (csrc/radius_graph.cu)."""
-        import ctypes as C
-        o, cell, d = self._grid_host(grid)
-        check(self.lib.distegnn_radius_count(N, ptr(x4), ptr(batch32), ptr(order32), ptr(cell_start),
-                                             C.cast(o, C.c_void_p), cell, C.cast(d, C.c_void_p), float(r), int(loop),
-                                             ptr(deg), self._s(x4)), "radius_count")
-        self.launches += 1 if N else 0
-
-    def radius_fill(self, N, x4, batch32, order32, cell_start, grid, r, loop, rowptr, row, col, dist) -> None:
-        import ctypes as C
-        o, cell, d = self._grid_host(grid)
-        check(self.lib.distegnn_radius_fill(N, ptr(x4), ptr(batch32), ptr(order32), ptr(cell_start),
-                                            C.cast(o, C.c_void_p), cell, C.cast(d, C.c_void_p), float(r), int(loop),
-                                            ptr(rowptr), ptr(row), ptr(col), ptr(dist), self._s(x4)), "radius_fill")
-        self.launches += 1 if N else 0
+    def virtual_layer_bwd_simt(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
+                               g_G, g_Xv, g_lp) -> None:
+        """fp32-FMA twin of virtual_layer_bwd (cross-check only); wT = the three matrices transposed, fp32."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_layer_bwd_simt(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn), ptr(Xv),
+                                                       ptr(G), ptr(lp), ptr(wT), ptr(g_agg_v), ptr(g_trans_v), ptr(g_vsum),
+                                                       ptr(g_Hn), ptr(g_xv), ptr(g_G), ptr(g_Xv), ptr(g_lp), self._s(x4)),
+              "virtual_layer_bwd_simt")
 
     def edge_layer_bwd_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
         """fp32-FMA twin of edge_layer_bwd (cross-check only)."""

@@ -1,4 +1,5 @@
-// Backward of the real<->virtual stage — fp32 FMA on the CUDA cores, correctness first.
+// Backward of the real<->virtual stage — fp32 FMA on the CUDA cores: the first, correctness-first kernel,
+// now behind distegnn_virtual_layer_bwd_simt as the twin of the tensor-core kernel (virtual_layer_bwd_tc.cu).
 // Differentiates what distegnn_virtual_layer_fwd computes (reference models/FastEGNN.py:252-253 virtual geometry,
 // :154-163 edge_mode_virtual, :180 / :191-193 / :207 / :220-223 virtual halves of the coordinate and feature models and
 // the global_mean_pool scatters; in the reference: autograd through [N,2H+1+C,C] and several [N,C,64] tensors).
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) virtual_layer_bwd_kernel(const Vi
 
 }  // namespace degnn
 
-extern "C" int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+extern "C" int distegnn_virtual_layer_bwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
                                           const int32_t* batch32, const float* x4, const float* Hn, const float* Xv,
                                           const float* G, const float* layer_params, const float* wT,
                                           const float* g_agg_v, const float* g_trans_v, const float* g_vsum,

@@ -527,7 +527,7 @@ class _FastEGNNFunction(torch.autograd.Function):
                 g_agg_m, g_agg_v = r[5].contiguous(), r[6].contiguous()
                 g_lps[i + 1] += r[7]
             # ---- 3. real<->virtual stage (CUDA) ------------------------------------------------------------------------
-            wT = torch.stack([lp[offs[k]:offs[k] + H * H].view(H, H).t().contiguous() for k in ("V_W2", "V_WXV", "V_WX")])
+            wT = be.virtual_bwd_prepare(A, Cn, Na, lp)           # operand images of the stage's weights for the tensor cores
             g_Hn_i, g_xv = torch.empty(N, H, device=dev), torch.empty(N, 4, device=dev)
             g_G_i, g_Xv_acc = zeros(B, Cn, H), g_Xv_i.contiguous().clone()
             be.virtual_layer_bwd((N, B, A, Cn, Na), S["flags"], st["batch32"], S["x4"], S["Hn"], S["Xv"], S["G"], lp, wT,

@@ -187,17 +187,29 @@ DISTEGNN_API int distegnn_virtual_layer_fwd_cs(int64_t n_nodes, int n_graphs, in
                                                 float* agg_v, float* trans_v, float* vsum, void* stream);
 
 /* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
- * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile.  Inputs: the forward inputs, wT = the three
- * 64x64 matrices V_W2, V_WXV, V_WX of the parameter block TRANSPOSED ([3][64][64], wT[m][n*64+k] = W_m[k*64+n]), and the
- * upstream gradients g_agg_v [N,64] (NULL with FLAG_LAST), g_trans_v [N,4], g_vsum [B,K] (entries [4:] are read; already
- * summed over the partitions).  g_Hn [N,64] and g_xv [N,4] are WRITTEN; g_G [B,C,64], g_Xv [B,3,C] and the parameter
- * gradients (V_W1R, V_W2, V_B2, V_WXV, V_BXV, V_W3XV, V_WX, V_BX, V_W3X of a parameter-layout buffer) are accumulated. */
+ * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile; the six row-wise tile GEMMs run on tcgen05.
+ * `weight_images` (96 KB, device): the stage's three 64x64 matrices and their transposes as fp16 hi/lo images in the
+ * shared-memory operand layout, written by distegnn_virtual_bwd_prepare(layer_params) — once per layer and call; the
+ * kernel streams them through shared memory with TMA.  Upstream gradients: g_agg_v [N,64] (NULL with FLAG_LAST), g_trans_v
+ * [N,4], g_vsum [B,K] (entries [4:] are read; already summed over the partitions).  g_Hn [N,64] and g_xv [N,4] are WRITTEN;
+ * g_G [B,C,64], g_Xv [B,3,C] and the parameter gradients (V_W1R, V_W2, V_B2, V_WXV, V_BXV, V_W3XV, V_WX, V_BX, V_W3X of a
+ * parameter-layout buffer) are accumulated. */
+DISTEGNN_API int distegnn_virtual_bwd_prepare(int A, int C, int Na, const float* layer_params, void* weight_images,
+                                              void* stream);
 DISTEGNN_API int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
                                             const int32_t* batch32, const float* x4, const float* Hn, const float* Xv,
-                                            const float* G, const float* layer_params, const float* wT,
+                                            const float* G, const float* layer_params, const void* weight_images,
                                             const float* g_agg_v, const float* g_trans_v, const float* g_vsum,
                                             float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
                                             void* stream);
+/* Same outputs with every tile GEMM as fp32 FMA on the CUDA cores (csrc/virtual_layer_bwd.cu; the first backward kernel,
+ * kept as a twin).  wT = the matrices V_W2, V_WXV, V_WX TRANSPOSED as fp32 ([3][64][64], wT[m][n*64+k] = W_m[k*64+n]). */
+DISTEGNN_API int distegnn_virtual_layer_bwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
+                                                 const int32_t* batch32, const float* x4, const float* Hn, const float* Xv,
+                                                 const float* G, const float* layer_params, const float* wT,
+                                                 const float* g_agg_v, const float* g_trans_v, const float* g_vsum,
+                                                 float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
+                                                 void* stream);
 
 /* On-device radius graph: replaces the host-side `radius_graph(pos_i, r=radius, max_num_neighbors=N)`
  * + `edge_attr = |dx|` of the reference's partitioners (datasets/distribute_graphs.py:43-44; PyG / torch_cluster).

@@ -163,6 +163,9 @@ class ShadowBackend:
         g_x4[:, :3] += gx
         g_lp += glp
 
+    def virtual_bwd_prepare(self, A, Cn, Na, lp):
+        return None
+
     def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
                           g_G, g_Xv, g_lp):
         from tests import shadow_autograd as sa

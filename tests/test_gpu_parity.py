@@ -663,7 +663,7 @@ def test_edge_stage_backward(flags, A):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,B,last", [(8, 1, False), (3, 5, False), (5, 1, True)])
+@pytest.mark.parametrize("C,B,last", [(8, 1, False), (3, 5, False), (5, 1, True), (16, 2, False), (1, 3, False)])
 def test_virtual_stage_backward(C, B, last):
     from distegnn_b200.backend import cuda_backend
     from tests import shadow_autograd as sa
@@ -692,19 +692,22 @@ def test_virtual_stage_backward(C, B, last):
     if not last:
         loss = loss + (av * g_aggv.double()).sum()
     rx, rH, rX, rG, rlp = torch.autograd.grad(loss, (xd, Hd, Xd, Gd, lpd))
-    # kernel
+    # kernels: the tensor-core production kernel and its fp32-FMA twin
     wT = torch.stack([lp[offs[k]:offs[k] + 4096].view(64, 64).t().contiguous() for k in ("V_W2", "V_WXV", "V_WX")])
-    gHn, gxv = torch.empty(N, 64, device=dev()), torch.empty(N, 4, device=dev())
-    gG, gXv, glp = torch.zeros_like(G), torch.zeros_like(Xv), torch.zeros_like(lp)
-    be.virtual_layer_bwd((N, B, A, C, Na), flags, batch, x4, Hn, Xv, G, lp, wT, None if last else g_aggv, g_tv, g_vsum,
-                         gHn, gxv, gG, gXv, glp)
-    torch.cuda.synchronize()
-    errs = dict(Hn=_rel(gHn, rH), x=_rel(gxv[:, :3], rx), G=_rel(gG, rG), Xv=_rel(gXv, rX))
-    for k in ("V_W1R", "V_W2", "V_B2", "V_WXV", "V_BXV", "V_W3XV", "V_WX", "V_BX", "V_W3X"):
-        n = 4096 if k in ("V_W2", "V_WXV", "V_WX") else 64
-        errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
-    print(f"virtual stage backward C={C} B={B} last={last}: rel err vs float64 autograd {errs}")
-    assert max(errs.values()) <= 2e-5
+    wimg = be.virtual_bwd_prepare(A, C, Na, lp)
+    for name, fn, w in (("tcgen05", be.virtual_layer_bwd, wimg), ("fp32-FMA twin", be.virtual_layer_bwd_simt, wT)):
+        gHn, gxv = torch.empty(N, 64, device=dev()), torch.empty(N, 4, device=dev())
+        gG, gXv, glp = torch.zeros_like(G), torch.zeros_like(Xv), torch.zeros_like(lp)
+        fn((N, B, A, C, Na), flags, batch, x4, Hn, Xv, G, lp, w, None if last else g_aggv, g_tv, g_vsum, gHn, gxv, gG, gXv,
+           glp)
+        torch.cuda.synchronize()
+        errs = dict(Hn=_rel(gHn, rH), x=_rel(gxv[:, :3], rx), G=_rel(gG, rG), Xv=_rel(gXv, rX))
+        for k in ("V_W1R", "V_W2", "V_B2", "V_WXV", "V_BXV", "V_W3XV", "V_WX", "V_BX", "V_W3X"):
+            n = 4096 if k in ("V_W2", "V_WXV", "V_WX") else 64
+            errs[k] = _rel(glp[offs[k]:offs[k] + n], rlp[offs[k]:offs[k] + n])
+        print(f"virtual stage backward [{name}] C={C} B={B} last={last}: rel err vs float64 autograd "
+              + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+        assert max(errs.values()) <= 2e-5, name
 
 
 # ---- the whole training path on the GPU: forward kernels + backward kernels + dense stages, against the reference's own
