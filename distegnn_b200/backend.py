@@ -119,6 +119,29 @@ class CudaBackend:
                                                        ptr(g_Hn), ptr(g_xv), ptr(g_G), ptr(g_Xv), ptr(g_lp), self._s(x4)),
               "virtual_layer_bwd_simt")
 
+    @staticmethod
+    def _grid_host(grid):
+        import ctypes as C
+        origin, cell, dims = grid
+        return (C.c_float * 3)(*origin), float(cell), (C.c_int32 * 3)(*dims)
+
+    def radius_count(self, N, x4, batch32, order32, cell_start, grid, r, loop, deg) -> None:
+        """Neighbour counts of the on-device radius graph (csrc/radius_graph.cu)."""
+        import ctypes as C
+        o, cell, d = self._grid_host(grid)
+        check(self.lib.distegnn_radius_count(N, ptr(x4), ptr(batch32), ptr(order32), ptr(cell_start),
+                                             C.cast(o, C.c_void_p), cell, C.cast(d, C.c_void_p), float(r), int(loop),
+                                             ptr(deg), self._s(x4)), "radius_count")
+        self.launches += 1 if N else 0
+
+    def radius_fill(self, N, x4, batch32, order32, cell_start, grid, r, loop, rowptr, row, col, dist) -> None:
+        import ctypes as C
+        o, cell, d = self._grid_host(grid)
+        check(self.lib.distegnn_radius_fill(N, ptr(x4), ptr(batch32), ptr(order32), ptr(cell_start),
+                                            C.cast(o, C.c_void_p), cell, C.cast(d, C.c_void_p), float(r), int(loop),
+                                            ptr(rowptr), ptr(row), ptr(col), ptr(dist), self._s(x4)), "radius_fill")
+        self.launches += 1 if N else 0
+
     def edge_layer_bwd_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
         """fp32-FMA twin of edge_layer_bwd (cross-check only)."""
         N, E, A, Cn, Na = dims

@@ -48,3 +48,22 @@ def test_host_only_entry_points():
         assert False
     except ValueError:
         pass
+
+
+def test_backend_has_every_method_the_host_code_calls():
+    """Static guard (no GPU): every `be.<method>(` used by the host-side modules exists on the CUDA backend class and on
+    the torch stand-in used by the CPU tests."""
+    import os
+    import re
+    from distegnn_b200 import backend
+    from tests.shadow_backend import ShadowBackend
+    root = os.path.dirname(os.path.abspath(backend.__file__))
+    used = set()
+    for f in ("fast_egnn.py", "graph.py"):
+        used |= set(re.findall(r"\bbe\.(\w+)\(", open(os.path.join(root, f)).read()))
+    cls = [v for v in vars(backend).values() if isinstance(v, type) and v.__name__.endswith("Backend")][0]
+    missing = sorted(m for m in used if not hasattr(cls, m))
+    assert not missing, f"CudaBackend lacks {missing}"
+    model_only = {m for m in used if m not in ("radius_count", "radius_fill")}      # graph.py is CUDA-only
+    missing = sorted(m for m in model_only if not hasattr(ShadowBackend, m))
+    assert not missing, f"ShadowBackend lacks {missing}"
