@@ -93,20 +93,30 @@ def main():
                                                 p64[0]["loc_mean"], normalize=w.normalize)
             loss = sum((refs[r] * cots[r].double()).sum() for r in range(world)) + world * (refX * cotX.double()).sum()
             rg = torch.autograd.grad(loss, [sd64[k] for k in names], allow_unused=True)
-            off, worst, wk = 0, 0.0, ""
-            for k, r_ in zip(names, rg):
+            # the same in float32: the reference arithmetic's own rounding noise on these (heavily cancelling) sums sets the
+            # scale of the gate — measured on this 8-partition case: 9e-4 on gcl_3.coord_mlp_v_virtual.0.bias
+            sd32 = {k: v.float().requires_grad_(True) for k, v in sd.items()}
+            r32, X32 = orc.forward_partitions(sd32, [{k: v for k, v in p.items() if k != "loc_mean"} for p in parts],
+                                              parts[0]["loc_mean"], normalize=w.normalize)
+            l32 = sum((r32[r] * cots[r]).sum() for r in range(world)) + world * (X32 * cotX).sum()
+            rg32 = torch.autograd.grad(l32, [sd32[k] for k in names], allow_unused=True)
+            off, worst, wk, wtol = 0, 0.0, "", 0.0
+            for k, r_, q_ in zip(names, rg, rg32):
                 n = sd[k].numel()
                 mine = flat[off:off + n].cpu().double().reshape(sd[k].shape)
                 off += n
                 if r_ is None or float(r_.abs().max()) == 0.0:
                     ok &= float(mine.abs().max()) == 0.0
                     continue
-                e = float((mine - r_).abs().max() / r_.abs().max())
-                if e > worst:
-                    worst, wk = e, k
-            print(f"gradients summed over {world} ranks vs float64 autograd through the partitioned oracle: worst "
-                  f"{wk} {worst:.3e}", flush=True)
-            ok &= worst <= 5e-4
+                den = float(r_.abs().max())
+                e = float((mine - r_).abs().max() / den)
+                noise = float((q_.double() - r_).abs().max() / den)
+                tol = max(2e-4, 3.0 * noise)
+                ok &= e <= tol
+                if e / tol > (worst / wtol if wtol else 0.0):
+                    worst, wk, wtol = e, k, tol
+            print(f"gradients summed over {world} ranks vs float64 autograd through the partitioned oracle: tightest "
+                  f"{wk} err {worst:.3e} (gate {wtol:.3e} = max(2e-4, 3 x the oracle's own fp32-vs-fp64 difference))", flush=True)
             print("DIST_GRAD_PARITY", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
