@@ -141,3 +141,98 @@ def test_two_partition_gradients_match_reference_world_size_2():
         print("rank", r, "worst", worst, "dead", len(dead))
         # protocol: L+1 packed collectives forward, L packed collectives backward (the reference: 6 per layer each way)
         assert res[r][3] == L + 1 and res[r][4] == L
+
+
+def test_inference_path_is_taken_without_grad():
+    """no_grad / frozen parameters -> the light inference path (no autograd node, nothing kept)."""
+    from distegnn_b200 import FastEGNN
+    from tests.shadow_backend import ShadowBackend
+    z, kw, sd = load_golden("fluid160_c5")
+    inp = golden_inputs(z)
+    m = FastEGNN(hidden_nf=64, world_size=1, **kw)
+    m.load_state_dict(sd)
+    m._backend = ShadowBackend()
+    with torch.no_grad():
+        out, X = m(**inp)
+    assert not out.requires_grad and not X.requires_grad
+    for p in m.parameters():
+        p.requires_grad_(False)
+    out2, X2 = m(**inp)
+    assert not out2.requires_grad and out2.grad_fn is None
+    assert torch.equal(out, out2) and torch.equal(X, X2)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    out3, X3 = m(**inp)                                   # training path: same numbers, attached to autograd
+    assert out3.requires_grad and out3.grad_fn is not None
+    assert float((out3 - out).abs().max()) <= 1e-6 and float((X3 - X).abs().max()) <= 1e-6
+
+
+def test_gradient_accumulation_and_optimizer_step():
+    """Two backward calls accumulate (utils/train.py:149-158 accumulates 4 micro-steps); Adam + clip_grad_norm_ run on the
+    module's own nn.Parameters and change the next forward."""
+    from distegnn_b200 import FastEGNN
+    from tests.shadow_backend import ShadowBackend
+    z, kw, sd = load_golden("fluid160_c5")
+    zg = load_grads("fluid160_c5")
+    inp = golden_inputs(z)
+    m = FastEGNN(hidden_nf=64, world_size=1, **kw)
+    m.load_state_dict(sd)
+    m._backend = ShadowBackend()
+    cot, cotX = torch.from_numpy(zg["cot.out"]).float(), torch.from_numpy(zg["cot.X"]).float()
+    for _ in range(2):
+        out, X = m(**inp)
+        ((out * cot).sum() + (X * cotX).sum()).backward()
+    for k, p in m.named_parameters():
+        ref = 2 * torch.from_numpy(zg["grad." + k])
+        if float(ref.abs().max()) > 0:
+            assert rel_err(p.grad, ref) <= 2e-4, k
+    out_before = m(**inp)[0].detach().clone()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 0.3)
+    opt.step()
+    out_after = m(**inp)[0].detach()
+    assert float((out_after - out_before).abs().max()) > 0
+
+
+def _ddp_rank(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from distegnn_b200 import FastEGNN
+        from tests.shadow_backend import ShadowBackend
+        z, kw, sd = load_golden(DIST_CASE)
+        zg = load_grads(DIST_CASE)
+        inp = golden_inputs(z, f"in{rank}.")
+        m = FastEGNN(hidden_nf=64, world_size=world, **kw)
+        m.load_state_dict(sd)
+        m._backend = ShadowBackend()
+        ddp = DistributedDataParallel(m, find_unused_parameters=True)      # reference main.py:196
+        node_attr = inp["node_attr"] if kw["node_attr_nf"] > 0 else None
+        out, X = ddp(inp["node_feat"], inp["node_loc"], inp["node_vel"], inp["loc_mean"], inp["edge_index"],
+                     inp["data_batch"], inp["edge_attr"], node_attr)        # positional, as utils/train.py:63-71
+        ((out * torch.from_numpy(zg[f"cot{rank}.out"])).sum() + (X * torch.from_numpy(zg["cot.X"])).sum()).backward()
+        q.put((rank, {k: p.grad.numpy() for k, p in m.named_parameters() if p.grad is not None}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_wrapper_averages_the_reference_rank_gradients():
+    """DistributedDataParallel(find_unused_parameters=True) around the module, as the reference wraps it: after backward
+    every rank holds the MEAN over ranks of the per-rank gradients — here the mean of the reference's own rank gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_rank, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    zg = load_grads(DIST_CASE)
+    for k, g0 in res[0][1].items():
+        ref = 0.5 * (torch.from_numpy(zg["grad0." + k]).double() + torch.from_numpy(zg["grad1." + k]).double())
+        assert np.array_equal(g0, res[1][1][k]), k                       # identical on both ranks
+        if float(ref.abs().max()) > 0:
+            assert rel_err(torch.from_numpy(g0), ref) <= 5e-4, k
