@@ -10,10 +10,13 @@ Per forward (L layers) the device work is
     L × { edge_layer, virtual_layer, node_layer → [all-reduce of the packed vsum] → virtual_update }
 i.e. ONE packed all-reduce per layer plus one up front (the reference issues 6 per layer, each behind
 host syncs: FastEGNN.py:196-197, 226-227, 260-261, 310-319).
+
+In grad mode the same kernels run with per-layer activations kept and the outputs are attached to autograd
+(``_FastEGNNFunction``): backward = hand-written kernels for the per-edge and real<->virtual stages, torch
+recompute for the dense per-node stages, one packed all-reduce of the statistics' gradient per layer.
 """
 from __future__ import annotations
 
-import warnings
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -199,7 +202,6 @@ class FastEGNN(nn.Module):
         self._graphs = _GraphCache()
         self._packed = None                # (key, tensors)
         self._timing = None                # bench.py: list collecting (name, start_evt, end_evt)
-        self._warned_grad = False
         self.cuda_graph = False            # opt-in: replay the forward as a CUDA graph (see _forward_graphed)
         self._graph_cache: Dict[tuple, tuple] = {}
         self._graph_max_captures = 8
