@@ -4,6 +4,6 @@ Public surface mirrors the reference: ``from distegnn_b200 import FastEGNN`` is 
 ``from models.FastEGNN import FastEGNN``.
 """
 from .fast_egnn import E_GCL_vel, FastEGNN  # noqa: F401
-from .graph import radius_graph  # noqa: F401  (on-device stand-in for torch_geometric.nn.radius_graph, SURVEY §8 f-2)
+from .graph import radius_graph, split_large_graph_random  # noqa: F401  (on-device graph construction, SURVEY §8 f-2)
 
-__all__ = ["FastEGNN", "E_GCL_vel", "radius_graph"]
+__all__ = ["FastEGNN", "E_GCL_vel", "radius_graph", "split_large_graph_random"]

@@ -75,3 +75,29 @@ def radius_graph(pos: Tensor, r: float, batch: Optional[Tensor] = None, loop: bo
     edge_index = torch.stack([row, col]).to(torch.int64)
     edge_attr = dist.unsqueeze(1).repeat(1, edge_attr_nf) if edge_attr_nf > 0 else dist.new_zeros(E, 0)
     return edge_index, edge_attr
+
+
+def split_large_graph_random(pos: Tensor, x: Tensor, target: Tensor, vel: Tensor, attr: Optional[Tensor], radius: float,
+                             world_size: int, special_nodes: Optional[Tensor] = None, generator=None):
+    """Device-side form of the reference's random partitioner (datasets/distribute_graphs.py:17-51): one host `randperm`
+    (same chunking: P−1 chunks of ⌊N/P⌋, remainder to the last), every chunk gets its own radius graph — built here with
+    the on-device `radius_graph` instead of PyG on the host — and `edge_attr` = the edge length in two columns (:44); every
+    partition carries the GLOBAL `loc_mean` (:32).  Returns a list of dicts with the reference's `Data` field names
+    (`x, pos, vel, attr, target, loc_mean, edge_index, edge_attr, special_nodes`); tensors stay on `pos.device`.
+    Pass `generator=torch.Generator().manual_seed(s)` to reproduce `torch.manual_seed(s)` + the reference's `randperm`."""
+    n = int(pos.shape[0])
+    idx = torch.randperm(n, generator=generator)                      # on the host, as the reference (device == 'cpu')
+    sizes = [n // world_size] * (world_size - 1)
+    sizes.append(n - sum(sizes))
+    chunks = torch.split(idx, sizes)
+    loc_mean = pos.mean(dim=0, keepdim=True)
+    if special_nodes is None:
+        special_nodes = torch.ones(n, dtype=torch.bool, device=pos.device)
+    out = []
+    for ch in chunks:
+        ch = ch.to(pos.device)
+        pos_i = pos[ch]
+        ei, ea = radius_graph(pos_i, radius, max_num_neighbors=int(pos_i.shape[0]))
+        out.append(dict(x=x[ch], pos=pos_i, vel=vel[ch], attr=None if attr is None else attr[ch], target=target[ch],
+                        loc_mean=loc_mean, edge_index=ei, edge_attr=ea, special_nodes=special_nodes[ch]))
+    return out
