@@ -169,7 +169,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// UMMA_WAIT_HINT_NS > 0: pass a suspend-time hint to try_wait — ptxas then emits TRYWAIT / NANOSLEEP.SYNCS / PHASECHK, the
+// warp sleeps until the phase completes (or the hint expires) instead of re-polling and stealing issue slots from the
+// warps that have work (polls were ~5 % of the edge kernel's instructions).
+#ifndef UMMA_WAIT_HINT_NS
+#define UMMA_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if UMMA_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"((uint32_t)UMMA_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -181,6 +200,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map), completes on an mbarrier ----------
