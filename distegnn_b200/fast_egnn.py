@@ -255,12 +255,17 @@ class FastEGNN(nn.Module):
         dev = node_loc.device
         be = self._get_backend(dev)
         A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
-        N, E, B = int(node_loc.shape[0]), int(edge_index.shape[1]), int(loc_mean.shape[0])
+        from .shards import CSRGraph
+        pre_csr = isinstance(edge_index, CSRGraph)           # graph already sorted by destination (shards.py, f-4)
+        N, B = int(node_loc.shape[0]), int(loc_mean.shape[0])
+        E = edge_index.num_edges if pre_csr else int(edge_index.shape[1])
+        if pre_csr and edge_index.num_nodes != N:
+            raise ValueError(f"CSRGraph has {edge_index.num_nodes} nodes, node_loc has {N}")
         if node_feat.shape != (N, F) or node_vel.shape != (N, 3) or node_loc.shape != (N, 3):
             raise ValueError(f"bad node tensor shapes: feat {tuple(node_feat.shape)}, loc "
                              f"{tuple(node_loc.shape)}, vel {tuple(node_vel.shape)}; expected N={N}, F={F}")
-        if edge_index.shape[0] != 2 or edge_index.dtype != torch.int64:
-            raise ValueError("edge_index must be int64 [2,E]")
+        if not pre_csr and (edge_index.shape[0] != 2 or edge_index.dtype != torch.int64):
+            raise ValueError("edge_index must be int64 [2,E] (or a distegnn_b200.shards.CSRGraph)")
         if data_batch.shape != (N,) or data_batch.dtype != torch.int64:
             raise ValueError("data_batch must be int64 [N]")
         if A > 0 and (edge_attr is None or edge_attr.shape != (E, A)):
@@ -278,8 +283,7 @@ class FastEGNN(nn.Module):
                                           edge_index, data_batch, edge_attr, node_attr)
         with torch.no_grad():
             pk = self._packed_params(dev)
-            rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
-            ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
+            rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
             args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
                         loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
                         data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
@@ -290,6 +294,18 @@ class FastEGNN(nn.Module):
             ws = self._alloc_workspace(dev, N, B, K)
             out, Xv = self._run(be, pk, dims, args, ws)
         return out, Xv
+
+    def _csr_inputs(self, be, edge_index, edge_attr, N: int, f32):
+        """(rowptr, row, col, edge_attr in CSR order): from the cache / a radix sort for an int64 edge_index, or straight
+        from a pre-sorted CSRGraph (shards.py) — then nothing is sorted or permuted."""
+        from .shards import CSRGraph
+        A = self.edge_attr_nf
+        if isinstance(edge_index, CSRGraph):
+            return (edge_index.rowptr.contiguous(), edge_index.rows().contiguous(), edge_index.col.contiguous(),
+                    f32(edge_attr) if A > 0 else None)
+        rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
+        ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
+        return rowptr, row, col, ea
 
     # ---- training path (SURVEY §8 f-1) -----------------------------------------------------------------
     def _forward_autograd(self, be, dev, dims, f32, node_feat, node_loc, node_vel, loc_mean, edge_index, data_batch,
@@ -306,8 +322,7 @@ class FastEGNN(nn.Module):
         emb_b = self.embedding_in.bias.to(device=dev, dtype=torch.float32)
         hv0 = self.virtual_node_feat[0].t().contiguous().to(device=dev, dtype=torch.float32)          # [C,64]
         with torch.no_grad():
-            rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
-            ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
+            rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
             args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
                         loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
                         data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)

@@ -911,3 +911,27 @@ def test_random_partitioner_on_device_matches_host_restatement():
                   if abs(float(np.linalg.norm(ref["node_loc"][e[0]].double().numpy() - ref["node_loc"][e[1]].double().numpy())) - w.radius) < 1e-6}
         assert (a ^ b) == border, (len(a), len(b))
         assert mine["edge_attr"].shape == (mine["edge_index"].shape[1], 2)
+
+
+@pytest.mark.gpu
+def test_shard_input_path_matches_edge_index_path(tmp_path):
+    """the pre-sorted CSR shard (int32 ids, edge_attr in CSR order, pinned host memory) fed straight to the
+    kernels — no radix sort, no permutation — gives the outputs of the int64 edge_index path."""
+    from distegnn_b200.shards import read_shard, shard_from_forward_inputs, write_shard
+    w = synth.WORKLOADS["fluid113k"]
+    host = synth.make_partitions(w, n_nodes=20_000, seed=8)[0]
+    sd = orc.init_state_dict(w.node_feat_nf, w.node_attr_nf, 2, 64, w.virtual_channels, 2, seed=6, coord_gain=0.05)
+    m = cuda_model(dict(node_feat_nf=w.node_feat_nf, node_attr_nf=w.node_attr_nf, edge_attr_nf=2,
+                        virtual_channels=w.virtual_channels, n_layers=2), sd)
+    p = str(tmp_path / "part0.shard")
+    write_shard(p, shard_from_forward_inputs(host))
+    sh = read_shard(p).pinned()
+    with torch.no_grad():
+        out_a, X_a = m(**to_dev(host))
+        builds = m._graphs.builds
+        out_b, X_b = m(**sh.to(dev()))
+        assert m._graphs.builds == builds                    # nothing was sorted for the shard
+    torch.cuda.synchronize()
+    assert max_abs(out_a, out_b) <= 2e-6 and max_abs(X_a, X_b) <= 2e-6
+    print(f"shard: {sh.nbytes() / 2**20:.1f} MiB on the wire vs "
+          f"{sum(v.numel() * v.element_size() for v in host.values() if v is not None) / 2**20:.1f} MiB for the tensors of the reference API")
