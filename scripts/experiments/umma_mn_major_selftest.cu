@@ -1,4 +1,4 @@
-// Experiment for the NEXT step of the backward pass (DESIGN.md §11): weight-gradient GEMMs D[n][k] = Σ_e G[e][n]·Act[e][k]
+// Experiment for the NEXT step of the backward pass (DESIGN.md §12): weight-gradient GEMMs D[n][k] = Σ_e G[e][n]·Act[e][k]
 // on tcgen05 with BOTH operands MN-major straight from row-major fp16 tiles [e][64] (128-byte rows, 16-byte chunk index
 // XORed with e mod 8 = the canonical SWIZZLE_128B MN-major layout), M = 64.
 // NOT part of the library (not under distegnn_b200/csrc, not built by build.py).  It has been compile-checked only:
