@@ -415,31 +415,41 @@ def run_ours(args, w, rank, world, local_rank):
             e3.record()
             barrier()
             t_pos = max_over_ranks(s3.elapsed_time(e3) * 1e-3 / n_e2e)
-            # pre-sorted CSR shard: int32 col + rowptr + CSR-ordered edge_attr from pinned memory, no sort
+            # pre-sorted CSR shard: int32 col + rowptr + CSR-ordered edge_attr from pinned memory, no sort.
+            # Local failures must not desynchronise the ranks: the collectives below run unconditionally.
             import tempfile
-            from distegnn_b200.shards import read_shard, shard_from_forward_inputs, write_shard
-            with tempfile.TemporaryDirectory() as td:
-                sp = os.path.join(td, f"rank{rank}.shard")
-                write_shard(sp, shard_from_forward_inputs(host))
-                shard = read_shard(sp).pinned()
+            t_shard_local, shard_bytes = float("nan"), 0
+            try:
+                from distegnn_b200.shards import read_shard, shard_from_forward_inputs, write_shard
+                with tempfile.TemporaryDirectory() as td:
+                    sp = os.path.join(td, f"rank{rank}.shard")
+                    write_shard(sp, shard_from_forward_inputs(host))
+                    shard = read_shard(sp).pinned()
+                shard_bytes = shard.nbytes()
 
-            def from_shard_step():
-                o, xv = model(**shard.to(dev))
-                out_host.copy_(o, non_blocking=True)
-                X_host.copy_(xv, non_blocking=True)
+                def from_shard_step():
+                    o, xv = model(**shard.to(dev))
+                    out_host.copy_(o, non_blocking=True)
+                    X_host.copy_(xv, non_blocking=True)
 
-            from_shard_step()
-            barrier()
-            s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s4.record()
-            for _ in range(n_e2e):
                 from_shard_step()
-            e4.record()
+                torch.cuda.synchronize()
+                s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s4.record()
+                for _ in range(n_e2e):
+                    from_shard_step()
+                e4.record()
+                torch.cuda.synchronize()
+                t_shard_local = s4.elapsed_time(e4) * 1e-3 / n_e2e
+            except Exception as ex:                       # noqa: BLE001 — reported in the JSON line, never fatal for the bench
+                print(f"[bench] from_shard leg failed on rank {rank}: {ex!r}", file=sys.stderr, flush=True)
             barrier()
-            t_shard = max_over_ranks(s4.elapsed_time(e4) * 1e-3 / n_e2e)
+            t_shard = max_over_ranks(t_shard_local if t_shard_local == t_shard_local else 1e30)
+            shard_bytes_total = int(sum_over_ranks(shard_bytes))
             e2e = {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
-                   "from_shard": {"value": 1.0 / t_shard, "ms_per_step": t_shard * 1e3,
-                                  "h2d_bytes_per_step": int(sum_over_ranks(shard.nbytes())),
+                   "from_shard": None if t_shard >= 1e29 else {
+                                  "value": 1.0 / t_shard, "ms_per_step": t_shard * 1e3,
+                                  "h2d_bytes_per_step": shard_bytes_total,
                                   "note": "inputs from the binary shard format (distegnn_b200/shards.py): graph already CSR "
                                           "by destination with int32 ids, edge_attr in CSR order; H2D, forward, D2H — no sort"},
                    "from_positions": {"value": 1.0 / t_pos, "ms_per_step": t_pos * 1e3,
