@@ -20,7 +20,7 @@ P_FIELDS = [
     "V_WX", "V_BX", "V_W3X", "L_W", "L_B", "L_W3", "L_B3", "N_W1", "N_B1", "N_W2", "N_B2",
     "M_W1", "M_B1", "M_W2", "M_B2",
 ]
-FLAG_NORMALIZE, FLAG_LAST, FLAG_INIT = 1, 2, 4
+FLAG_NORMALIZE, FLAG_LAST, FLAG_INIT, FLAG_ZERO_VSUM, FLAG_ZERO_AGG = 1, 2, 4, 8, 16
 MAX_CHANNELS, MAX_EDGE_ATTR, MAX_NODE_ATTR, MAX_NODE_FEAT, HIDDEN = 16, 8, 8, 16, 64
 
 _i64, _i32, _u32, _vp = C.c_int64, C.c_int, C.c_uint, C.c_void_p
@@ -30,30 +30,27 @@ SIGNATURES = {
     "distegnn_abi_version": [],
     "distegnn_param_layout": [_i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)],
     "distegnn_csr_workspace_bytes": [_i64, _i64, C.POINTER(_i64)],
-    "distegnn_build_csr": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "distegnn_build_csr": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "distegnn_gather_rows": [_vp, _vp, _i64, _i32, _vp, _vp],
-    "distegnn_embed_fwd": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
-    "distegnn_embed_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 14,
+    "distegnn_embed_fwd": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 15,
     "distegnn_edge_layer_fwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
-    "distegnn_edge_layer_bwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
     "distegnn_virtual_layer_bwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
-    "distegnn_virtual_layer_bwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
     "distegnn_virtual_bwd_prepare": [_i32, _i32, _i32, _vp, _vp, _vp],
     "distegnn_radius_count": [_i64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, _i32, _vp, _vp],
     "distegnn_radius_fill": [_i64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, _i32, _vp, _vp, _vp, _vp, _vp],
-    "distegnn_edge_layer_fwd_t16": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_edge_layer_fwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_edge_layer_fwd_tf32": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_selftest_umma": [_vp, _vp, _vp, _i32, _vp],
     "distegnn_virtual_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_virtual_layer_fwd_cs": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_virtual_layer_fwd_tf32": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_virtual_layer_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_node_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 20,
-    "distegnn_node_layer_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 20,
-    "distegnn_virtual_update_fwd": [_i32, _i32, _i32, _i32, _u32] + [_vp] * 7,
+    "distegnn_virtual_update_fwd": [_i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
+    "distegnn_comm_handle_bytes": [],
+    "distegnn_comm_init": [_i32, _i32, _i32, _i32, C.POINTER(_vp), _vp],
+    "distegnn_comm_connect": [_vp, _vp],
+    "distegnn_comm_set_timeout_ms": [_vp, _i64],
+    "distegnn_comm_status": [_vp, C.POINTER(_i32)],
+    "distegnn_comm_destroy": [_vp],
+    "distegnn_allreduce_packed": [_vp, _vp, _i64, _vp],
 }
+ABI_VERSION = 2
 
 _lib: Optional[C.CDLL] = None
 
@@ -78,6 +75,9 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.distegnn_last_error.argtypes = []
     lib.distegnn_last_error.restype = C.c_char_p
+    if lib.distegnn_abi_version() != ABI_VERSION:
+        raise DistEGNNError(f"{LIB_PATH} has ABI version {lib.distegnn_abi_version()}, this package needs {ABI_VERSION} — "
+                            "rebuild it with `python -m distegnn_b200.build --force`")
     _lib = lib
     return lib
 

@@ -33,7 +33,10 @@ class CudaBackend:
         return _lib.stream_ptr(t.device)
 
     # ---- graph preprocessing -------------------------------------------------------------------
-    def build_csr(self, edge_index: Tensor, n_nodes: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    def build_csr(self, edge_index: Tensor, n_nodes: int, validate: bool = True
+                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """int64 COO -> int32 CSR by destination.  `validate`: read back the out-of-range counter (one host sync per
+        build; builds are cached per edge_index) and raise ValueError like the reference's index assert would."""
         E = int(edge_index.shape[1])
         dev = edge_index.device
         stream = self._s(edge_index)
@@ -44,9 +47,12 @@ class CudaBackend:
         nbytes = C.c_int64(0)
         check(self.lib.distegnn_csr_workspace_bytes(n_nodes, E, C.byref(nbytes)), "csr_workspace_bytes")
         ws = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=dev)
+        bad = torch.empty(1, dtype=torch.int32, device=dev) if validate else None
         check(self.lib.distegnn_build_csr(ptr(edge_index), n_nodes, E, ptr(rowptr), ptr(row), ptr(col),
-                                          ptr(perm), ptr(ws), ws.numel(), stream), "build_csr")
-        self.launches += 5 if E else 1
+                                          ptr(perm), ptr(ws), ws.numel(), ptr(bad), stream), "build_csr")
+        self.launches += (5 if E else 1) + (1 if validate else 0)
+        if validate and E and int(bad.item()) != 0:
+            raise ValueError(f"edge_index has {int(bad.item())} edge(s) with a node id outside [0, {n_nodes})")
         return rowptr, row, col, perm
 
     def gather_rows(self, src: Tensor, perm: Tensor) -> Tensor:
@@ -59,22 +65,14 @@ class CudaBackend:
 
     # ---- layer stages --------------------------------------------------------------------------
     def embed(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
-              Hn, vsum) -> None:
+              Hn, vsum, n_invalid=None) -> None:
+        """`n_invalid`: zeroed int32 [1] device counter of data_batch entries that are unsorted / outside [0,B)."""
         N, B, F, A, Cn, Na = dims
         check(self.lib.distegnn_embed_fwd(N, B, F, A, Cn, Na, ptr(node_feat), ptr(node_loc),
                                           ptr(data_batch), ptr(emb_wt), ptr(emb_b), ptr(layer0), ptr(h),
                                           ptr(x4), ptr(batch32), ptr(P), ptr(Q), ptr(Hn), ptr(vsum),
-                                          self._s(h)), "embed_fwd")
+                                          ptr(n_invalid), self._s(h)), "embed_fwd")
         self.launches += 1 if N else 0
-
-    def embed_simt(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
-                   Hn, vsum) -> None:
-        """fp32-FMA twin of embed (cross-check only)."""
-        N, B, F, A, Cn, Na = dims
-        check(self.lib.distegnn_embed_fwd_simt(N, B, F, A, Cn, Na, ptr(node_feat), ptr(node_loc),
-                                               ptr(data_batch), ptr(emb_wt), ptr(emb_b), ptr(layer0), ptr(h),
-                                               ptr(x4), ptr(batch32), ptr(P), ptr(Q), ptr(Hn), ptr(vsum),
-                                               self._s(h)), "embed_fwd_simt")
 
     def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
         N, E, A, Cn, Na = dims
@@ -110,15 +108,6 @@ class CudaBackend:
               "virtual_layer_bwd")
         self.launches += 1 if N else 0
 
-    def virtual_layer_bwd_simt(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
-                               g_G, g_Xv, g_lp) -> None:
-        """fp32-FMA twin of virtual_layer_bwd (cross-check only); wT = the three matrices transposed, fp32."""
-        N, B, A, Cn, Na = dims
-        check(self.lib.distegnn_virtual_layer_bwd_simt(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn), ptr(Xv),
-                                                       ptr(G), ptr(lp), ptr(wT), ptr(g_agg_v), ptr(g_trans_v), ptr(g_vsum),
-                                                       ptr(g_Hn), ptr(g_xv), ptr(g_G), ptr(g_Xv), ptr(g_lp), self._s(x4)),
-              "virtual_layer_bwd_simt")
-
     @staticmethod
     def _grid_host(grid):
         import ctypes as C
@@ -142,61 +131,12 @@ class CudaBackend:
                                             ptr(rowptr), ptr(row), ptr(col), ptr(dist), self._s(x4)), "radius_fill")
         self.launches += 1 if N else 0
 
-    def edge_layer_bwd_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
-        """fp32-FMA twin of edge_layer_bwd (cross-check only)."""
-        N, E, A, Cn, Na = dims
-        check(self.lib.distegnn_edge_layer_bwd_simt(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea), ptr(x4),
-                                                    ptr(P), ptr(Q), ptr(lp), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P),
-                                                    ptr(g_Q), ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd_simt")
-
-    def edge_layer_t16(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
-        """thread-per-row tcgen05 twin of edge_layer (cross-check / A-B timing only)."""
-        N, E, A, Cn, Na = dims
-        check(self.lib.distegnn_edge_layer_fwd_t16(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
-                                                   ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
-                                                   ptr(agg_x), self._s(x4)), "edge_layer_fwd_t16")
-
-    def edge_layer_simt(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
-        """fp32-FMA twin of edge_layer (cross-check only; FastEGNN.forward never calls it)."""
-        N, E, A, Cn, Na = dims
-        check(self.lib.distegnn_edge_layer_fwd_simt(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
-                                                    ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
-                                                    ptr(agg_x), self._s(x4)), "edge_layer_fwd_simt")
-
     def virtual_layer(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
         N, B, A, Cn, Na = dims
         check(self.lib.distegnn_virtual_layer_fwd(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
                                                   ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
                                                   ptr(vsum), self._s(x4)), "virtual_layer_fwd")
         self.launches += 1 if N else 0
-
-    def edge_layer_tf32(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
-        """3xTF32 tensor-core twin of edge_layer (cross-check / A-B timing only)."""
-        N, E, A, Cn, Na = dims
-        check(self.lib.distegnn_edge_layer_fwd_tf32(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
-                                                    ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m),
-                                                    ptr(agg_x), self._s(x4)), "edge_layer_fwd_tf32")
-
-    def virtual_layer_cs(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
-        """thread-per-row tcgen05 twin of virtual_layer (cross-check / A-B timing only)."""
-        N, B, A, Cn, Na = dims
-        check(self.lib.distegnn_virtual_layer_fwd_cs(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
-                                                      ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
-                                                      ptr(vsum), self._s(x4)), "virtual_layer_fwd_cs")
-
-    def virtual_layer_tf32(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
-        """3xTF32 tensor-core twin of virtual_layer (cross-check / A-B timing only)."""
-        N, B, A, Cn, Na = dims
-        check(self.lib.distegnn_virtual_layer_fwd_tf32(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
-                                                       ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
-                                                       ptr(vsum), self._s(x4)), "virtual_layer_fwd_tf32")
-
-    def virtual_layer_simt(self, dims, flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vsum) -> None:
-        """fp32-FMA twin of virtual_layer (cross-check only)."""
-        N, B, A, Cn, Na = dims
-        check(self.lib.distegnn_virtual_layer_fwd_simt(N, B, A, Cn, Na, flags, ptr(batch32), ptr(x4), ptr(Hn),
-                                                       ptr(Xv), ptr(G), ptr(lp), ptr(agg_v), ptr(trans_v),
-                                                       ptr(vsum), self._s(x4)), "virtual_layer_fwd_simt")
 
     def node_layer(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
                    lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum) -> None:
@@ -208,22 +148,60 @@ class CudaBackend:
                                                ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd")
         self.launches += 1 if N else 0
 
-    def node_layer_simt(self, dims, flags, rowptr, batch32, h, x4, vel, attr, agg_m, agg_x, agg_v, trans_v,
-                        lp, lp_next, h_out, x4_out, P, Q, Hn, loc_out, vsum) -> None:
-        """fp32-FMA twin of node_layer (cross-check only)."""
-        N, B, A, Cn, Na = dims
-        check(self.lib.distegnn_node_layer_fwd_simt(N, B, A, Cn, Na, flags, ptr(rowptr), ptr(batch32), ptr(h),
-                                                    ptr(x4), ptr(vel), ptr(attr), ptr(agg_m), ptr(agg_x),
-                                                    ptr(agg_v), ptr(trans_v), ptr(lp), ptr(lp_next),
-                                                    ptr(h_out), ptr(x4_out), ptr(P), ptr(Q), ptr(Hn),
-                                                    ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd_simt")
-
-    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G) -> None:
+    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G, init_loc_mean=None, init_hv0=None,
+                       comm: "Optional[Comm]" = None) -> None:
+        """Virtual-node update; with `comm` the same kernel first all-reduces vsum over the partitions (NVLink peer
+        memory) — the fused form of weighted_average_reduce + update."""
         B, A, Cn, Na = dims
         check(self.lib.distegnn_virtual_update_fwd(B, A, Cn, Na, flags, ptr(vsum), ptr(Xv), ptr(Hv),
-                                                   ptr(lp), ptr(lp_next), ptr(G), self._s(vsum)),
+                                                   ptr(lp), ptr(lp_next), ptr(G), ptr(init_loc_mean), ptr(init_hv0),
+                                                   comm.handle if comm is not None else None, self._s(vsum)),
               "virtual_update_fwd")
         self.launches += 1 if B else 0
+
+    def allreduce_packed(self, comm: "Comm", buf: Tensor) -> None:
+        """In-place SUM of `buf` over the partitions through the communicator's peer-mapped segments."""
+        check(self.lib.distegnn_allreduce_packed(comm.handle, ptr(buf), buf.numel(), self._s(buf)), "allreduce_packed")
+        self.launches += 1 if buf.numel() else 0
+
+
+class Comm:
+    """Communicator of the virtual-node sync (C ABI: distegnn_comm_*).  One per (process group, capacity).  The IPC
+    handles are all-gathered with torch.distributed (plumbing); the exchange itself is the library's own kernel."""
+
+    def __init__(self, lib, device: torch.device, group, max_slots: int, slot_floats: int):
+        import torch.distributed as dist
+        self.lib, self.group, self.handle = lib, group, None
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.max_slots, self.slot_floats = int(max_slots), int(slot_floats)
+        nb = lib.distegnn_comm_handle_bytes()
+        mine = (C.c_ubyte * nb)()
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.distegnn_comm_init(self.rank, self.world, self.max_slots, self.slot_floats, C.byref(h), mine),
+                  "comm_init")
+            self.handle = h
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine), group=group)
+            allh = (C.c_ubyte * (nb * self.world)).from_buffer_copy(b"".join(gathered))
+            rc = lib.distegnn_comm_connect(self.handle, allh)
+            # every rank must agree on the outcome: a half-connected group would dead-lock in the first exchange
+            oks = [None] * self.world
+            dist.all_gather_object(oks, rc == 0, group=group)
+            if not all(oks):
+                msg = lib.distegnn_last_error().decode("utf-8", "replace") if rc != 0 else "a peer failed to connect"
+                self.destroy()
+                raise _lib.DistEGNNError(f"comm_connect failed: {msg}")
+
+    def status(self) -> int:
+        v = C.c_int(0)
+        check(self.lib.distegnn_comm_status(self.handle, C.byref(v)), "comm_status")
+        return int(v.value)
+
+    def destroy(self) -> None:
+        if self.handle is not None:
+            self.lib.distegnn_comm_destroy(self.handle)
+            self.handle = None
 
 
 _cuda_backend: Optional[CudaBackend] = None

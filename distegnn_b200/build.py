@@ -1,8 +1,12 @@
-"""Build libdistegnn_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""Build the CUDA libraries in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python -m distegnn_b200.build [--force] [--verbose]
 
-The shared library is git-ignored but travels to the GPU box with the gpurun snapshot.
+  libdistegnn_b200.so          the product: every entry point of include/distegnn_b200.h (csrc/*.cu)
+  libdistegnn_b200_testing.so  cross-check twins of include/distegnn_b200_testing.h (csrc/testing/*.cu); loaded only by
+                               tests/twin_backend.py and the A/B scripts, never by the package
+
+The shared libraries are git-ignored but travel to the GPU box with the gpurun snapshot.
 """
 from __future__ import annotations
 
@@ -10,76 +14,85 @@ import argparse
 import concurrent.futures as cf
 import os
 import subprocess
-import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
+TSRC = os.path.join(CSRC, "testing")
 ROOT = os.path.dirname(PKG)
+INC = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libdistegnn_b200.so")
+LIB_TESTING = os.path.join(PKG, "libdistegnn_b200_testing.so")
 OBJ = os.path.join(CSRC, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+          "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", CSRC]
+# shared by both libraries (error string, parameter layout, device queries)
+COMMON = ["api.cu"]
 
 
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def testing_sources():
+    return sorted(os.path.join("testing", f) for f in os.listdir(TSRC) if f.endswith(".cu"))
+
+
 def _deps_mtime():
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    hdrs.append(os.path.join(ROOT, "include", "distegnn_b200.h"))
+    hdrs += [os.path.join(INC, f) for f in os.listdir(INC) if f.endswith(".h")]
     return max(os.path.getmtime(h) for h in hdrs)
 
 
 def _compile(src, verbose, objdir=None, defs=None):
-    obj = os.path.join(objdir or OBJ, src[:-3] + ".o")
+    obj = os.path.join(objdir or OBJ, src.replace(os.sep, "_")[:-3] + ".o")
     extra = os.environ.get("DISTEGNN_NVCC_DEFS", "").split() + list(defs or [])   # e.g. "-DT16_CHUNK_UNROLL=4"
+    if src.startswith("testing" + os.sep):        # the twins' declarations (default visibility) come from the testing header
+        extra += ["-include", os.path.join(INC, "distegnn_b200_testing.h")]
     cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")
-    log = p.stderr
     with open(obj + ".ptxas.log", "w") as f:
-        f.write(log)
+        f.write(p.stderr)
     if verbose:
-        print(log)
+        print(p.stderr)
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
-    srcs = sources()
-    newest = max([os.path.getmtime(os.path.join(CSRC, s)) for s in srcs] + [_deps_mtime(),
-                                                                          os.path.getmtime(__file__)])
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
-        return LIB
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared",
-           "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
-    p = subprocess.run(cmd, capture_output=True, text=True)
+def _link(lib, objs):
+    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "shared",
+                        "-Xlinker", "-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
-    return LIB
+    return lib
+
+
+def _build_into(objdir, lib, lib_testing, verbose, defs=None):
+    os.makedirs(objdir, exist_ok=True)
+    srcs, tsrcs = sources(), testing_sources()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs) + len(tsrcs))) as ex:
+        objs = dict(zip(srcs + tsrcs, ex.map(lambda s: _compile(s, verbose, objdir, defs), srcs + tsrcs)))
+    _link(lib, [objs[s] for s in srcs])
+    _link(lib_testing, [objs[s] for s in COMMON] + [objs[s] for s in tsrcs])
+    return lib
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in sources() + testing_sources()]
+    newest = max([os.path.getmtime(s) for s in srcs] + [_deps_mtime(), os.path.getmtime(__file__)])
+    if not force and all(os.path.exists(l) and os.path.getmtime(l) >= newest for l in (LIB, LIB_TESTING)):
+        return LIB
+    return _build_into(OBJ, LIB, LIB_TESTING, verbose)
 
 
 def build_variant(tag: str, defs, verbose: bool = False) -> str:
     """A/B build: the same sources with extra -D flags -> distegnn_b200/variants/libdistegnn_b200.<tag>.so
     (select it at run time with DISTEGNN_B200_LIB=<path>; the variants travel to the GPU box like the main .so)."""
     vdir = os.path.join(PKG, "variants")
-    objdir = os.path.join(vdir, "build_" + tag)
-    os.makedirs(objdir, exist_ok=True)
-    srcs = sources()
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose, objdir, defs), srcs))
-    lib = os.path.join(vdir, f"libdistegnn_b200.{tag}.so")
-    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "shared",
-                        "-Xlinker", "-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
-    if p.returncode != 0:
-        raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
-    return lib
+    return _build_into(os.path.join(vdir, "build_" + tag), os.path.join(vdir, f"libdistegnn_b200.{tag}.so"),
+                       os.path.join(vdir, f"libdistegnn_b200_testing.{tag}.so"), verbose, defs)
 
 
 if __name__ == "__main__":

@@ -8,11 +8,16 @@
 
 namespace degnn {
 
-__global__ void csr_keys_kernel(const int64_t* __restrict__ edge_index, int64_t E, int32_t* keys,
-                                int32_t* vals) {
+// Ids outside [0,N) are counted into *n_invalid (the reference fails with a device-side index assert on such input) and
+// clamped, so nothing downstream can index out of bounds before the host has looked at the counter.
+__global__ void csr_keys_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N, int32_t* keys,
+                                int32_t* vals, int32_t* n_invalid) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < E) {
-        keys[e] = (int32_t)edge_index[e];   // row = edge_index[0, e]
+        const int64_t r = edge_index[e], c = edge_index[E + e];   // row = edge_index[0, e], col = edge_index[1, e]
+        const bool bad = r < 0 || r >= N || c < 0 || c >= N;
+        if (bad && n_invalid) atomicAdd(n_invalid, 1);
+        keys[e] = (int32_t)(r < 0 ? 0 : (r >= N ? N - 1 : r));
         vals[e] = (int32_t)e;
     }
 }
@@ -24,7 +29,8 @@ __global__ void csr_finish_kernel(const int64_t* __restrict__ edge_index, int64_
                                   int32_t* __restrict__ col, int32_t* __restrict__ rowptr) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < E) {
-        col[e] = (int32_t)edge_index[E + perm[e]];
+        const int64_t c = edge_index[E + perm[e]];
+        col[e] = (int32_t)(c < 0 ? 0 : (c >= N ? N - 1 : c));
         int32_t r = row[e];
         int32_t prev = (e == 0) ? -1 : row[e - 1];
         for (int32_t k = prev + 1; k <= r; ++k) rowptr[k] = (int32_t)e;
@@ -86,12 +92,16 @@ int distegnn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t* byte
 
 int distegnn_build_csr(const int64_t* edge_index, int64_t n_nodes, int64_t n_edges, int32_t* rowptr,
                        int32_t* row, int32_t* col, int32_t* perm, void* workspace,
-                       int64_t workspace_bytes, void* stream_) {
+                       int64_t workspace_bytes, int32_t* n_invalid, void* stream_) {
     using namespace degnn;
     cudaStream_t stream = (cudaStream_t)stream_;
     DEGNN_CHECK_ARG(rowptr, "null rowptr");
     DEGNN_CHECK_ARG(n_nodes >= 0 && n_nodes < INT32_MAX, "n_nodes out of int32 range");
     DEGNN_CHECK_ARG(n_edges >= 0 && n_edges < INT32_MAX, "n_edges out of int32 range");
+    if (n_invalid) {
+        fill_i32_kernel<<<1, 32, 0, stream>>>(n_invalid, 1, 0);
+        DEGNN_CHECK_LAUNCH();
+    }
     if (n_edges == 0) {
         int64_t n = n_nodes + 1;
         fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rowptr, n, 0);
@@ -99,6 +109,7 @@ int distegnn_build_csr(const int64_t* edge_index, int64_t n_nodes, int64_t n_edg
         return DISTEGNN_OK;
     }
     DEGNN_CHECK_ARG(edge_index && row && col && perm && workspace, "null pointer");
+    DEGNN_CHECK_ARG(n_nodes > 0, "edges on an empty node set");
     int64_t need = 0;
     if (int rc = distegnn_csr_workspace_bytes(n_nodes, n_edges, &need)) return rc;
     if (workspace_bytes < need) {
@@ -114,7 +125,7 @@ int distegnn_build_csr(const int64_t* edge_index, int64_t n_nodes, int64_t n_edg
     sort_temp_bytes(n_nodes, n_edges, &tmp_bytes);
 
     unsigned blocks = (unsigned)((n_edges + 255) / 256);
-    csr_keys_kernel<<<blocks, 256, 0, stream>>>(edge_index, n_edges, keys, vals);
+    csr_keys_kernel<<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, keys, vals, n_invalid);
     DEGNN_CHECK_LAUNCH();
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const int32_t*)keys, row,
                                                     (const int32_t*)vals, perm, (int)n_edges, 0,

@@ -531,20 +531,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
 
 }  // namespace degnn
 
-extern "C" int distegnn_edge_layer_fwd_t16(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
-                                           const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
-                                           const float* x4, const float* P, const float* Q,
-                                           const float* layer_params, float* agg_m, float* agg_x, void* stream);
-
 extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q,
                                        const float* layer_params, float* agg_m, float* agg_x, void* stream) {
     using namespace degnn;
-#ifdef DISTEGNN_EDGE_DEFAULT_T16      // A/B builds: route the production symbol to the thread-per-row twin
-    return distegnn_edge_layer_fwd_t16(n_nodes, n_edges, A, C, Na, flags, row, col, edge_attr_sorted, x4, P, Q,
-                                       layer_params, agg_m, agg_x, stream);
-#endif
     if (int rc = check_dims(A, C, Na)) return rc;
     if (n_edges == 0) return DISTEGNN_OK;
     DEGNN_CHECK_ARG(n_nodes > 0 && n_edges > 0, "negative size");

@@ -40,7 +40,8 @@ constexpr int NT_SMEM_BYTES = (2 * NT_W + 6 * NT_W + 2 * NT_W + 2 * 3 * NT_W) * 
                               + NT_GROUPS * TILE_M * NT_ROW * 4                      // staging rows
                               + (5 * H + DISTEGNN_MAX_NODE_ATTR * H) * 4             // lb, lw3, nb1, nb2, nxb1, N1d
                               + NT_GROUPS * 8 * 4                                    // accS[4] + sg[2] (+pad) per group
-                              + 128;                                                 // mbarriers + tmem base
+                              + 128                                                  // mbarriers + tmem base
+                              + 256;                                                 // a zero row (FLAG_ZERO_AGG)
 constexpr uint32_t NT_LBO64 = 1024, NT_LBO192 = 3072;
 
 __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const NodeTcArgs a) {
@@ -64,10 +65,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     float* acc_all = n1ds + DISTEGNN_MAX_NODE_ATTR * H;          // per group: accS[4], sg[2] (as int), pad[2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(acc_all + NT_GROUPS * 8);   // [2 groups][2]: staging, mma
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * NT_GROUPS);
+    float* zero_row = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // 256 B of zeros, 16-byte aligned
 
     const int tid = threadIdx.x;
     const int grp = tid >> 7, t = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
     const bool last = a.flags & DISTEGNN_FLAG_LAST;
+    const bool zero_agg = a.flags & DISTEGNN_FLAG_ZERO_AGG;   // leave agg_m / agg_x zeroed for the next edge stage
     const int Na = a.Na;
 
     // ---- one-time setup ---------------------------------------------------------------------------
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     if (!last)
         for (int i = tid; i < Na * H; i += NT_THREADS) n1ds[i] = a.n1[(size_t)3 * H * H + i];
     if (tid < NT_GROUPS * 8) acc_all[tid] = 0.f;
+    if (tid < H) zero_row[tid] = 0.f;
     if (tid == 0) {
         for (int i = 0; i < 2 * NT_GROUPS; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
         if (valid) {
             x = ldg4(a.x4 + node * 4);
             ax = ldg4(a.agg_x + node * 4);
+            if (zero_agg) *reinterpret_cast<float4*>(const_cast<float*>(a.agg_x) + node * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             tv = ldg4(a.trans_v + node * 4);
             v0 = __ldg(a.vel + node * 3);
             v1 = __ldg(a.vel + node * 3 + 1);
@@ -268,8 +273,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
 
         // ---- node MLP layer 1, chunks 2 and 3: agg_m / deg, agg_v  (D2 accumulates with one row scale) ----------
         float s2 = s_h;                              // scale the D2 row currently carries
-        auto l1_chunk = [&](float rs, uint64_t bhi, uint64_t blo, const float* next_src) {
+        auto l1_chunk = [&](float rs, uint64_t bhi, uint64_t blo, const float* next_src, float* zero_dst) {
             staged();
+            if (zero_dst && valid) {                  // the staged row is in shared memory: its source can be cleared
+                bulk_s2g(zero_dst + node * H, zero_row, H * 4);
+                bulk_commit();
+            }
             const float sn = tc16::encode_row_s(
                 [&](int c, float (&v)[16], bool) {
 #pragma unroll
@@ -304,8 +313,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
             else stage_tile(a.h, tile + tstride);    // staging buffer is idle for the rest of this tile: prefetch h
             mma_done();
         };
-        l1_chunk(invdeg, desc(N1hi + NT_W, NT_LBO64), desc(N1lo + NT_W, NT_LBO64), a.agg_v);
-        l1_chunk(1.0f, desc(N1hi + 2 * NT_W, NT_LBO64), desc(N1lo + 2 * NT_W, NT_LBO64), nullptr);
+        l1_chunk(invdeg, desc(N1hi + NT_W, NT_LBO64), desc(N1lo + NT_W, NT_LBO64), a.agg_v,
+                 zero_agg ? const_cast<float*>(a.agg_m) : nullptr);
+        l1_chunk(1.0f, desc(N1hi + 2 * NT_W, NT_LBO64), desc(N1lo + 2 * NT_W, NT_LBO64), nullptr, nullptr);
 
         // ---- t1 = SiLU(D2/s + attr·N1d + b1) -> A;  D1 = t1·N2ᵀ ----------------------------------------------
         float attrv[DISTEGNN_MAX_NODE_ATTR];
@@ -393,6 +403,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     }
     named_bar(bar_id, NT_GROUP);
     if (cur_graph >= 0 && t < 4) atomicAdd(a.vsum + (size_t)cur_graph * a.K + t, accS[t]);
+    if (zero_agg) bulk_wait_all();                   // this thread's zero-row stores have left shared memory
 
     fence_before_sync();
     __syncthreads();
@@ -411,6 +422,7 @@ struct EmbedTcArgs {
     const float* wt; const float* bias;                                  // [F][64], [64]
     const float* nw1a; const float* nxb1; const float* nw1b; const float* nw1h;
     float* h; float* x4; int32_t* batch32; float* P; float* Q; float* Hn; float* vsum;
+    int32_t* n_invalid;                                                   // device counter of bad data_batch entries (or null)
 };
 constexpr int ET_SMEM_BYTES = 2 * 3 * NT_W * 2 + (DISTEGNN_MAX_NODE_FEAT + 2) * H * 4 + NT_GROUPS * 8 * 4 + 64;
 
@@ -475,7 +487,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) embed_tc_kernel(const EmbedTcAr
 #pragma unroll
         for (int k = 0; k < DISTEGNN_MAX_NODE_FEAT; ++k) f[k] = (valid && k < F) ? __ldg(a.feat + node * F + k) : 0.f;
         if (valid) {
-            g = (int)a.batch64[node];
+            // precondition of every per-graph reduction downstream: ids sorted and inside [0,B) (PyG batches are; the
+            // reference takes B from data_batch[-1]+1, FastEGNN.py:298).  Violations are counted for the host and clamped.
+            const int64_t gi = a.batch64[node];
+            const bool bad = gi < 0 || gi >= a.B || (node > 0 && a.batch64[node - 1] > gi);
+            if (bad && a.n_invalid) atomicAdd(a.n_invalid, 1);
+            g = (int)(gi < 0 ? 0 : (gi >= a.B ? a.B - 1 : gi));
             a.batch32[node] = g;
             const float* p = a.loc + node * 3;
             xv = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
@@ -629,7 +646,8 @@ extern "C" int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int
 extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na, const float* node_feat,
                                   const float* node_loc, const int64_t* data_batch, const float* emb_wt,
                                   const float* emb_b, const float* layer0_params, float* h, float* x4,
-                                  int32_t* batch32, float* P, float* Q, float* Hn, float* vsum, void* stream) {
+                                  int32_t* batch32, float* P, float* Q, float* Hn, float* vsum, int32_t* n_invalid,
+                                  void* stream) {
     using namespace degnn;
     if (int rc = check_dims(A, C, Na)) return rc;
     if (n_nodes == 0) return DISTEGNN_OK;
@@ -646,6 +664,7 @@ extern "C" int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, i
     a.nw1b = layer0_params + L.off[DISTEGNN_P_E_W1B];
     a.nw1h = layer0_params + L.off[DISTEGNN_P_V_W1H];
     a.h = h; a.x4 = x4; a.batch32 = batch32; a.P = P; a.Q = Q; a.Hn = Hn; a.vsum = vsum;
+    a.n_invalid = n_invalid;
     ensure_dynamic_smem((const void*)embed_tc_kernel, (int)ET_SMEM_BYTES);
     const int64_t tiles = (n_nodes + TILE_M - 1) / TILE_M;
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;

@@ -301,87 +301,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) node_layer_kernel(const NodeArgs 
     if (cur_graph >= 0 && tid < 4) atomicAdd(a.vsum + (size_t)cur_graph * a.K + tid, accS[tid]);
 }
 
-// =================================================================================================
-// virtual-node update: one CTA per graph, 256 threads
-// =================================================================================================
-struct VUpdArgs {
-    int B, C, K;
-    unsigned flags;
-    const float* vsum;
-    float* Xv;   // [B,3,C]
-    float* Hv;   // [B,C,64]
-    const float* m1; const float* mb1; const float* m2; const float* mb2;   // node_mlp_virtual
-    const float* nv1v; const float* nv1m; const float* nvb1;                 // next layer's W1v_V, W1v_M, b1v
-    float* G;    // [B,C,64]
-};
-
-__global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs a) {
-    constexpr int MC = DISTEGNN_MAX_CHANNELS;
-    __shared__ float sX[3 * MC];        // new Xv [3][C]
-    __shared__ float sZ[3 * MC];        // Xv − x̄
-    __shared__ float sM[MC * MC];       // m_X
-    __shared__ float sHv[MC * H];       // Hv (old, then new) [C][64]
-    __shared__ float sAg[MC * H];       // mean mv [C][64]
-    __shared__ float sT[MC * H];        // hidden of node_mlp_virtual
-    const int b = blockIdx.x, tid = threadIdx.x, C = a.C;
-    const float* vs = a.vsum + (size_t)b * a.K;
-    const bool init = a.flags & DISTEGNN_FLAG_INIT;
-    const bool last = a.flags & DISTEGNN_FLAG_LAST;
-    const float inv = 1.0f / fmaxf(vs[3], 1.0f);
-
-    if (tid < 3 * C) {
-        float x = a.Xv[(size_t)b * 3 * C + tid];
-        if (!init) x += vs[4 + tid] * inv;
-        sX[tid] = x;
-        a.Xv[(size_t)b * 3 * C + tid] = x;
-        sZ[tid] = x - vs[tid / C] * inv;   // tid / C = spatial dim
-    }
-    if (last) return;
-    for (int i = tid; i < C * H; i += NTHREADS) {
-        sHv[i] = a.Hv[(size_t)b * C * H + i];
-        sAg[i] = init ? 0.f : vs[4 + 3 * C + i] * inv;
-    }
-    __syncthreads();
-    if (tid < C * C) {
-        const int i = tid / C, j = tid - i * C;
-        sM[tid] = sZ[i] * sZ[j] + sZ[C + i] * sZ[C + j] + sZ[2 * C + i] * sZ[2 * C + j];
-    }
-    if (!init) {
-        // Hv' = Hv + W2·SiLU(W1·[Hv; agg] + b1) + b2   (per channel; thread per (c, n))
-        for (int i = tid; i < C * H; i += NTHREADS) {
-            const int c = i / H, n = i - c * H;
-            float s = __ldg(a.mb1 + n);
-            for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.m1 + k * H + n), s);
-            for (int k = 0; k < H; ++k) s = fmaf(sAg[c * H + k], __ldg(a.m1 + (H + k) * H + n), s);
-            sT[i] = silu(s);
-        }
-        __syncthreads();
-        float upd[(MC * H + NTHREADS - 1) / NTHREADS];
-        int u = 0;
-        for (int i = tid; i < C * H; i += NTHREADS, ++u) {
-            const int c = i / H, n = i - c * H;
-            float s = __ldg(a.mb2 + n);
-            for (int k = 0; k < H; ++k) s = fmaf(sT[c * H + k], __ldg(a.m2 + k * H + n), s);
-            upd[u] = sHv[i] + s;
-        }
-        __syncthreads();
-        u = 0;
-        for (int i = tid; i < C * H; i += NTHREADS, ++u) {
-            sHv[i] = upd[u];
-            a.Hv[(size_t)b * C * H + i] = upd[u];
-        }
-    }
-    __syncthreads();
-    // G[c][n] = Σ_k W1v_V[k][n]·Hv'[c][k] + Σ_j W1v_M[j][n]·m_X[j][c] + b1v[n]
-    for (int i = tid; i < C * H; i += NTHREADS) {
-        const int c = i / H, n = i - c * H;
-        float s = __ldg(a.nvb1 + n);
-        for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.nv1v + k * H + n), s);
-        for (int j = 0; j < C; ++j) s = fmaf(sM[j * C + c], __ldg(a.nv1m + j * H + n), s);
-        a.G[(size_t)b * C * H + i] = s;
-    }
-}
-
 }  // namespace degnn
 
 // =================================================================================================
@@ -460,36 +379,6 @@ extern "C" int distegnn_node_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A
     int64_t grid = (int64_t)sm_count() * 2;
     if (grid > tiles) grid = tiles;
     node_layer_kernel<<<(unsigned)grid, NTHREADS, NODE_SMEM_BYTES, (cudaStream_t)stream>>>(a);
-    DEGNN_CHECK_LAUNCH();
-    return DISTEGNN_OK;
-}
-
-extern "C" int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na, unsigned flags,
-                                           const float* vsum, float* Xv, float* Hv,
-                                           const float* layer_params, const float* next_layer_params,
-                                           float* G, void* stream) {
-    using namespace degnn;
-    if (int rc = check_dims(A, C, Na)) return rc;
-    if (n_graphs == 0) return DISTEGNN_OK;
-    const bool last = flags & DISTEGNN_FLAG_LAST, init = flags & DISTEGNN_FLAG_INIT;
-    DEGNN_CHECK_ARG(n_graphs > 0, "bad size");
-    DEGNN_CHECK_ARG(vsum && Xv, "null pointer");
-    DEGNN_CHECK_ARG(last || (Hv && next_layer_params && G), "null pointer (non-last)");
-    DEGNN_CHECK_ARG(last || init || layer_params, "null layer_params");
-    Layout L = make_layout(A, C, Na);
-    VUpdArgs a;
-    a.B = n_graphs; a.C = C; a.K = 4 + 3 * C + H * C; a.flags = flags;
-    a.vsum = vsum; a.Xv = Xv; a.Hv = Hv;
-    const float* lp = layer_params ? layer_params : next_layer_params;
-    a.m1 = lp ? lp + L.off[DISTEGNN_P_M_W1] : nullptr;
-    a.mb1 = lp ? lp + L.off[DISTEGNN_P_M_B1] : nullptr;
-    a.m2 = lp ? lp + L.off[DISTEGNN_P_M_W2] : nullptr;
-    a.mb2 = lp ? lp + L.off[DISTEGNN_P_M_B2] : nullptr;
-    a.nv1v = next_layer_params ? next_layer_params + L.off[DISTEGNN_P_V_W1V] : nullptr;
-    a.nv1m = next_layer_params ? next_layer_params + L.off[DISTEGNN_P_V_W1M] : nullptr;
-    a.nvb1 = next_layer_params ? next_layer_params + L.off[DISTEGNN_P_V_B1] : nullptr;
-    a.G = G;
-    virtual_update_kernel<<<(unsigned)n_graphs, NTHREADS, 0, (cudaStream_t)stream>>>(a);
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;
 }

@@ -211,6 +211,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// ---- bulk async copy shared -> global (TMA engine), tracked by the issuing thread's bulk async-group --------------
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- per-thread async copies global -> shared (LDGSTS: per-lane addresses, no registers, generic proxy) ------------
 // Completion is per issuing thread (commit_group / wait_group); a thread that only reads what it copied itself needs
 // no barrier.  16-byte form bypasses L1 (.cg); the 4/8-byte forms allocate in L1 (.ca is the only variant).

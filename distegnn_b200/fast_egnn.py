@@ -6,10 +6,14 @@ checkpoints work unchanged — but ``forward`` runs entirely in the hand-written
 the C ABI (include/distegnn_b200.h).  There is no eager/CPU fallback.
 
 Per forward (L layers) the device work is
-    embed → [all-reduce] → virtual_update(INIT)
-    L × { edge_layer, virtual_layer, node_layer → [all-reduce of the packed vsum] → virtual_update }
-i.e. ONE packed all-reduce per layer plus one up front (the reference issues 6 per layer, each behind
-host syncs: FastEGNN.py:196-197, 226-227, 260-261, 310-319).
+    embed → sync+virtual_update(INIT)
+    L × { edge_layer, virtual_layer, node_layer → sync+virtual_update }
+i.e. 2 + 4L kernel launches and nothing else: ONE exchange of the packed statistics per layer plus one up front
+(the reference issues 6 NCCL calls per layer, each behind host syncs: FastEGNN.py:196-197, 226-227, 260-261,
+310-319), fused into the virtual-node update kernel as a push over NVLink peer memory (csrc/comm.cuh; when
+CUDA IPC between the ranks is not available the exchange is a `torch.distributed` all-reduce instead).  No memset or
+copy launches (the consumers clear `vsum` / `agg_*` for the next layer), so the whole forward — collectives
+included — replays as one CUDA graph (`model.cuda_graph = True`), for any world size.
 
 In grad mode the same kernels run with per-layer activations kept and the outputs are attached to autograd
 (``_FastEGNNFunction``): backward = hand-written kernels for the per-edge and real<->virtual stages, torch
@@ -131,14 +135,14 @@ class _GraphCache:
         self.entries: "OrderedDict[int, tuple]" = OrderedDict()
         self.builds = 0
 
-    def get(self, backend, edge_index: Tensor, n_nodes: int):
+    def get(self, backend, edge_index: Tensor, n_nodes: int, validate: bool = True):
         key = id(edge_index)
         hit = self.entries.get(key)
         if hit is not None and hit[0] is edge_index and hit[1] == edge_index._version and hit[2] == n_nodes:   # noqa: E501
             self.entries.move_to_end(key)
             return hit[3]
         ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
-        csr = backend.build_csr(ei, n_nodes)
+        csr = backend.build_csr(ei, n_nodes, validate)
         self.builds += 1
         self.entries[key] = (edge_index, edge_index._version, n_nodes, csr)
         while len(self.entries) > self.capacity:
@@ -206,6 +210,12 @@ class FastEGNN(nn.Module):
         self._graph_cache: Dict[tuple, tuple] = {}
         self._graph_max_captures = 8
         self.process_group = None          # torch.distributed group for the virtual-node sync (None = WORLD)
+        self.validate_inputs = True        # check edge ids / data_batch once per distinct tensor (one host sync each)
+        self._validated_batch = None       # (tensor, version, N, B) of the last data_batch that passed
+        self._workspaces: Dict[tuple, Dict[str, Tensor]] = {}
+        self._keep_state = None            # tests: a list that receives the training-path forward's saved state
+        self._comm = None                  # backend.Comm | False (peer exchange unavailable: torch.distributed instead)
+        self._comm_key = None
 
     # ---- runtime helpers -----------------------------------------------------------------------
     def _get_backend(self, device: torch.device):
@@ -234,10 +244,53 @@ class FastEGNN(nn.Module):
         self._packed = (key, packed)
         return packed
 
-    def _sync_virtual(self, vsum: Tensor) -> None:
+    def _get_comm(self, be, dev: torch.device, B: int, K: int):
+        """Communicator of the virtual-node sync for calls of [B,K] floats, or None (single partition / stand-in
+        backend / no peer access: then `_sync_virtual` goes through torch.distributed).  Creation is collective."""
+        if self.world_size == 1 or self._backend is not None or dev.type != "cuda":
+            return None
+        import os
+        import torch.distributed as dist
+        if self._comm is False or os.environ.get("DISTEGNN_B200_COMM", "p2p") == "nccl":
+            return None
+        if self._comm is not None and self._comm_key[0] >= B and self._comm_key[1] >= K:
+            return self._comm
+        from .backend import Comm
+        if self._comm is not None:                       # capacity grows: all ranks see the same B, K
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.process_group)
+            self._comm.destroy()
+            self._comm = None
+            self._graph_cache.clear()
+        try:
+            self._comm = Comm(be.lib, dev, self.process_group, max(B, 1), K)
+            self._comm_key = (max(B, 1), K)
+        except _lib.DistEGNNError as e:
+            import warnings
+            warnings.warn(f"distegnn_b200: peer-memory exchange unavailable ({e}); the virtual-node sync uses "
+                          "torch.distributed all_reduce", RuntimeWarning)
+            self._comm = False
+            return None
+        return self._comm
+
+    def release_comm(self) -> None:
+        """Collective teardown of the peer-memory communicator (call on every rank, e.g. before destroying the process
+        group); captured CUDA graphs that reference it are dropped.  A later forward creates a new one."""
+        if self._comm:
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.process_group)       # nobody unmaps while a peer still has an exchange in flight
+            self._comm.destroy()
+        self._comm, self._comm_key = None, None
+        self._graph_cache.clear()
+
+    def _sync_virtual(self, vsum: Tensor, be=None, comm=None) -> None:
         """weighted_average_reduce (FastEGNN.py:310-319) on the packed statistics: one SUM all-reduce;
         the division by the summed node count happens in virtual_update."""
         if self.world_size > 1:
+            if comm is not None:
+                be.allreduce_packed(comm, vsum)
+                return
             import torch.distributed as dist
             dist.all_reduce(vsum, op=dist.ReduceOp.SUM, group=self.process_group)
 
@@ -277,23 +330,55 @@ class FastEGNN(nn.Module):
         K = 4 + 3 * Cn + H * Cn
         f32 = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) \
             else t.detach().to(dtype=torch.float32).contiguous()
+        if pre_csr:
+            edge_index.validate(dev)
+        import contextlib
+        guard = torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+        with guard:                                           # launches and smem opt-ins happen on the tensors' device
+            if training_path:
+                for name, t in (("node_feat", node_feat), ("node_loc", node_loc), ("node_vel", node_vel),
+                                ("edge_attr", edge_attr), ("node_attr", node_attr)):
+                    if t is not None and t.requires_grad:
+                        import warnings
+                        warnings.warn(f"distegnn_b200.FastEGNN: `{name}` requires grad, but the fused path treats inputs "
+                                      "as constants (the reference trains weights only, utils/train.py:149-158): no "
+                                      "gradient will flow to it", RuntimeWarning, stacklevel=2)
+                return self._forward_autograd(be, dev, (N, E, B, K), f32, node_feat, node_loc, node_vel, loc_mean,
+                                              edge_index, data_batch, edge_attr, node_attr)
+            with torch.no_grad():
+                pk = self._packed_params(dev)
+                rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
+                args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
+                            loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
+                            data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
+                dims = (N, E, B, K)
+                comm = self._get_comm(be, dev, B, K)
+                graph_ok = self.world_size == 1 or comm is not None      # NCCL calls are not captured
+                if self.cuda_graph and graph_ok and self._backend is None and dev.type == "cuda" \
+                        and self._timing is None and self._batch_checked(args["data_batch"], N, B):
+                    return self._forward_graphed(be, pk, dims, args, comm)
+                ws = self._workspace(dev, N, B, K)
+                # results go straight into fresh tensors (no copy launch); everything else lives in the workspace
+                return self._run(be, pk, dims, args, ws, comm,
+                                 out=torch.empty(N, 3, dtype=torch.float32, device=dev),
+                                 Xv=torch.empty(B, 3, Cn, dtype=torch.float32, device=dev))
 
-        if training_path:
-            return self._forward_autograd(be, dev, (N, E, B, K), f32, node_feat, node_loc, node_vel, loc_mean,
-                                          edge_index, data_batch, edge_attr, node_attr)
-        with torch.no_grad():
-            pk = self._packed_params(dev)
-            rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
-            args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
-                        loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
-                        data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
-            dims = (N, E, B, K)
-            if self.cuda_graph and self.world_size == 1 and self._backend is None and dev.type == "cuda" \
-                    and self._timing is None:
-                return self._forward_graphed(be, pk, dims, args)
-            ws = self._alloc_workspace(dev, N, B, K)
-            out, Xv = self._run(be, pk, dims, args, ws)
-        return out, Xv
+    def _batch_checked(self, data_batch: Tensor, N: int, B: int) -> bool:
+        v = self._validated_batch
+        return (not self.validate_inputs) or (v is not None and v[0] is data_batch and v[1] == data_batch._version
+                                              and v[2] == N and v[3] == B)
+
+    def _check_batch(self, counter: Optional[Tensor], data_batch: Tensor, N: int, B: int) -> None:
+        """Read the embed kernel's counter of unsorted / out-of-range data_batch entries (one host sync per distinct
+        data_batch tensor) and raise like the reference's scatter would on an out-of-range id."""
+        if counter is None:
+            return
+        bad = int(counter.item())
+        if bad:
+            raise ValueError(f"data_batch has {bad} entr{'y' if bad == 1 else 'ies'} that are not non-decreasing or "
+                             f"lie outside [0, {B}) (B = loc_mean.shape[0]); PyG batches are sorted and the fused "
+                             "per-graph reductions rely on it")
+        self._validated_batch = (data_batch, data_batch._version, N, B)
 
     def _csr_inputs(self, be, edge_index, edge_attr, N: int, f32):
         """(rowptr, row, col, edge_attr in CSR order): from the cache / a radix sort for an int64 edge_index, or straight
@@ -303,7 +388,7 @@ class FastEGNN(nn.Module):
         if isinstance(edge_index, CSRGraph):
             return (edge_index.rowptr.contiguous(), edge_index.rows().contiguous(), edge_index.col.contiguous(),
                     f32(edge_attr) if A > 0 else None)
-        rowptr, row, col, perm = self._graphs.get(be, edge_index, N)
+        rowptr, row, col, perm = self._graphs.get(be, edge_index, N, self.validate_inputs)
         ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
         return rowptr, row, col, ea
 
@@ -341,14 +426,18 @@ class FastEGNN(nn.Module):
         Hv = hv0.unsqueeze(0).expand(B, Cn, H).contiguous()
         h, x4, batch32, P, Q, Hn = new(N, H), new(N, 4), new(N, dt=torch.int32), new(N, H), new(N, H), new(N, H)
         vsum = zeros(B, K)
+        comm = self._get_comm(be, dev, B, K)
+        counter = None if self._batch_checked(a["data_batch"], N, B) else torch.zeros(1, dtype=torch.int32, device=dev)
         be.embed((N, B, F, A, Cn, Na), a["node_feat"], a["node_loc"], a["data_batch"], emb_wt, emb_b,
-                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
-        st = dict(batch32=batch32, vsum_init=vsum, layers=[])
+                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum, counter)
+        self._check_batch(counter, a["data_batch"], N, B)
+        st = dict(batch32=batch32, vsum_init=vsum, layers=[], comm=comm)
         if L == 0:
             return a["node_loc"].clone(), Xv, st
-        self._sync_virtual(vsum)
+        if comm is None:
+            self._sync_virtual(vsum)
         G = new(B, Cn, H)
-        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
+        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G, comm=comm)
         out = None
         for i in range(L):
             last = i == L - 1
@@ -364,51 +453,80 @@ class FastEGNN(nn.Module):
             out = new(N, 3) if last else None
             be.node_layer((N, B, A, Cn, Na), flags, a["rowptr"], batch32, h, x4, a["node_vel"], a["attr"], agg_m,
                           agg_x, agg_v, trans_v, lp, lp_next, hn, x4n, Pn, Qn, Hnn, out, vs)
-            self._sync_virtual(vs)
+            if comm is None:
+                self._sync_virtual(vs)
             st["layers"].append(dict(h=h, x4=x4, P=P, Q=Q, Hn=Hn, Xv=Xv, Hv=Hv, G=G, agg_m=agg_m, agg_x=agg_x,
                                      agg_v=agg_v, trans_v=trans_v, vsum=vs, flags=flags))
             Xv, Hv = Xv.clone(), (Hv if last else Hv.clone())
             Gn = None if last else new(B, Cn, H)
-            be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vs, Xv, Hv, lp, lp_next, Gn)
+            # with a communicator the update kernel all-reduces `vs` first and leaves the summed statistics in it
+            be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vs, Xv, Hv, lp, lp_next, Gn, comm=comm)
             h, x4, P, Q, Hn, G = hn, x4n, Pn, Qn, Hnn, Gn
+        if self._keep_state is not None:
+            self._keep_state.append(st)
         return out, Xv, st
 
     # ---- device work ---------------------------------------------------------------------------
-    def _alloc_workspace(self, dev, N: int, B: int, K: int) -> Dict[str, Tensor]:
-        Cn = self.virtual_channels
-        new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
-        return dict(h=new(N, H), P=new(N, H), Q=new(N, H), Hn=new(N, H), agg_m=new(N, H), agg_v=new(N, H),
-                    x4=new(N, 4), agg_x=new(N, 4), trans_v=new(N, 4), batch32=new(N, dt=torch.int32),
-                    vsum=new(B, K), G=new(B, Cn, H), Xv=new(B, 3, Cn), Hv=new(B, Cn, H), out=new(N, 3))
+    def _workspace(self, dev, N: int, B: int, K: int) -> Dict[str, Tensor]:
+        """Per-shape buffers of the inference path, kept between calls.  `vsum`, `agg_m`, `agg_x` are accumulators: they
+        start zeroed and every forward leaves them zeroed again (the consuming kernels clear them), so no memset is
+        launched in steady state.  A forward that raised half-way marks the set dirty and it is re-zeroed."""
+        key = (str(dev), N, B, K)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            Cn = self.virtual_channels
+            new = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+            zeros = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            ws = dict(h=new(N, H), P=new(N, H), Q=new(N, H), Hn=new(N, H), agg_m=zeros(N, H), agg_v=new(N, H),
+                      x4=new(N, 4), agg_x=zeros(N, 4), trans_v=new(N, 4), batch32=new(N, dt=torch.int32),
+                      vsum=zeros(B, K), G=new(B, Cn, H), Xv=new(B, 3, Cn), Hv=new(B, Cn, H), out=new(N, 3),
+                      counter=torch.zeros(1, dtype=torch.int32, device=dev), dirty=False)
+            while len(self._workspaces) >= 4:
+                self._workspaces.pop(next(iter(self._workspaces)))
+            self._workspaces[key] = ws
+        return ws
 
-    def _run(self, be, pk, dims, a: Dict[str, Tensor], ws: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
-        """Enqueue one forward on the current stream (buffers in `ws`; nothing allocates, nothing syncs)."""
+    def _run(self, be, pk, dims, a: Dict[str, Tensor], ws: Dict[str, Tensor], comm=None, out: Optional[Tensor] = None,
+             Xv: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """Enqueue one forward on the current stream: 2 + 4L kernel launches (buffers in `ws`; nothing allocates,
+        nothing syncs unless a new data_batch tensor has to be validated).  Results are written to `out` / `Xv`
+        (default: the workspace's own buffers, which the next forward overwrites)."""
         A, Cn, Na, F = self.edge_attr_nf, self.virtual_channels, self.node_attr_nf, self.node_feat_nf
         N, E, B, K = dims
         layers: List[Tensor] = pk["layers"]
         h, P, Q, Hn, agg_m, agg_v = ws["h"], ws["P"], ws["Q"], ws["Hn"], ws["agg_m"], ws["agg_v"]
         x4, agg_x, trans_v, batch32 = ws["x4"], ws["agg_x"], ws["trans_v"], ws["batch32"]
-        vsum, G, Xv, Hv, out = ws["vsum"], ws["G"], ws["Xv"], ws["Hv"], ws["out"]
-        Xv.copy_(a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn))                     # FastEGNN.py:300
-        Hv.copy_(pk["hv0"].unsqueeze(0).expand(B, Cn, H))                          # FastEGNN.py:299 (as [B,C,64])
-        vsum.zero_()
+        vsum, G, Hv = ws["vsum"], ws["G"], ws["Hv"]
+        out = ws["out"] if out is None else out
+        Xv = ws["Xv"] if Xv is None else Xv
+        if ws["dirty"]:
+            vsum.zero_(); agg_m.zero_(); agg_x.zero_()
+        ws["dirty"] = True
         base = _lib.FLAG_NORMALIZE if self.normalize else 0
         L = self.n_layers
+        counter = None
+        if not self._batch_checked(a["data_batch"], N, B):
+            counter = ws["counter"]
+            counter.zero_()
         be.embed((N, B, F, A, Cn, Na), a["node_feat"], a["node_loc"], a["data_batch"], pk["emb_wt"], pk["emb_b"],
-                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum)
+                 layers[0] if L else None, h, x4, batch32, P, Q, Hn, vsum, counter)
+        self._check_batch(counter, a["data_batch"], N, B)
         if L == 0:
+            vsum.zero_()
             out.copy_(a["node_loc"])
+            Xv.copy_(a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn))
+            ws["dirty"] = False
             return out, Xv
-        self._sync_virtual(vsum)
-        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT, vsum, Xv, Hv, None, layers[0], G)
+        sync = comm is None and self.world_size > 1              # torch.distributed path (stand-in backend / no P2P)
+        if sync:
+            self._sync_virtual(vsum)
+        # FastEGNN.py:299-300 (initial Hv, Xv) are folded into the INIT update
+        be.virtual_update((B, A, Cn, Na), _lib.FLAG_INIT | _lib.FLAG_ZERO_VSUM, vsum, Xv, Hv, None, layers[0], G,
+                          a["loc_mean"], pk["hv0"], comm)
         for i in range(L):
             last = i == L - 1
             flags = base | (_lib.FLAG_LAST if last else 0)
             lp, lp_next = layers[i], (None if last else layers[i + 1])
-            agg_x.zero_()
-            vsum.zero_()
-            if not last:
-                agg_m.zero_()
             t0 = self._mark("edge")
             be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp,
                           None if last else agg_m, agg_x)
@@ -416,41 +534,47 @@ class FastEGNN(nn.Module):
             be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp,
                              None if last else agg_v, trans_v, vsum)
             t2 = self._mark("virtual_end")
-            be.node_layer((N, B, A, Cn, Na), flags, a["rowptr"], batch32, h, x4, a["node_vel"], a["attr"],
-                          None if last else agg_m, agg_x, None if last else agg_v, trans_v, lp, lp_next,
+            be.node_layer((N, B, A, Cn, Na), flags | _lib.FLAG_ZERO_AGG, a["rowptr"], batch32, h, x4, a["node_vel"],
+                          a["attr"], None if last else agg_m, agg_x, None if last else agg_v, trans_v, lp, lp_next,
                           None if last else h, x4, None if last else P, None if last else Q,
                           None if last else Hn, out if last else None, vsum)
             t3 = self._mark("node_end")
+            if sync:
+                self._sync_virtual(vsum)
+            be.virtual_update((B, A, Cn, Na), (flags & ~_lib.FLAG_NORMALIZE) | _lib.FLAG_ZERO_VSUM, vsum, Xv, Hv, lp,
+                              lp_next, G, comm=comm)
+            t4 = self._mark("update_end")
             if self._timing is not None:
-                self._timing.append((i, t0[1], t1[1], t2[1], t3[1]))
-            self._sync_virtual(vsum)
-            be.virtual_update((B, A, Cn, Na), flags & ~_lib.FLAG_NORMALIZE, vsum, Xv, Hv, lp, lp_next, G)
+                self._timing.append((i, t0[1], t1[1], t2[1], t3[1], t4[1]))
+        ws["dirty"] = False
         return out, Xv
 
-    def _forward_graphed(self, be, pk, dims, a: Dict[str, Tensor]) -> Tuple[Tensor, Tensor]:
-        """CUDA-graph replay of `_run` (opt-in: `model.cuda_graph = True`; single-partition only — capturing the
-        NCCL all-reduce of the multi-partition path is not supported in this release).  The graph is keyed by the addresses and
-        shapes of every tensor it reads, so it is valid for as long as the caller keeps passing the same (possibly
+    def _forward_graphed(self, be, pk, dims, a: Dict[str, Tensor], comm=None) -> Tuple[Tensor, Tensor]:
+        """CUDA-graph replay of `_run` (opt-in: `model.cuda_graph = True`).  Works for any world size when the
+        virtual-node sync is the library's own peer-memory exchange (it is part of the update kernels, so the graph holds
+        the collectives too; every rank must replay — same call sequence as eager).  The graph is keyed by the addresses
+        and shapes of every tensor it reads, so it is valid for as long as the caller keeps passing the same (possibly
         in-place updated) tensors — inference loops, rollouts, benchmarks.  New tensors trigger a re-capture; after
         `_graph_max_captures` distinct keys the model falls back to eager launches for unseen keys."""
-        key = (dims, id(pk)) + tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in a.items() if v is not None)
+        key = (dims, id(pk), id(comm)) + tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in a.items() if v is not None)
         ent = self._graph_cache.get(key)
+        dev = a["node_loc"].device
         if ent is None:
+            ws = self._workspace(dev, dims[0], dims[2], dims[3])
             if len(self._graph_cache) >= self._graph_max_captures:
-                ws = self._alloc_workspace(a["node_loc"].device, dims[0], dims[2], dims[3])
-                return self._run(be, pk, dims, a, ws)
-            dev = a["node_loc"].device
-            ws = self._alloc_workspace(dev, dims[0], dims[2], dims[3])
+                out, Xv = self._run(be, pk, dims, a, ws, comm)
+                return out.clone(), Xv.clone()
+            # warm-up run + capture run: both are real forwards on every rank (the exchange inside stays matched)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):            # warm-up outside capture: lazy inits, NCCL communicator
-                self._run(be, pk, dims, a, ws)
+            with torch.cuda.stream(side):            # warm-up outside capture: lazy inits (smem opt-ins)
+                self._run(be, pk, dims, a, ws, comm)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             n0 = be.launches
             with torch.cuda.graph(g):
-                self._run(be, pk, dims, a, ws)
+                self._run(be, pk, dims, a, ws, comm)
             ent = (g, ws, be.launches - n0, a, pk)   # keep the keyed tensors alive: their addresses are baked in
             self._graph_cache[key] = ent
         ent[0].replay()
@@ -520,8 +644,7 @@ class _FastEGNNFunction(torch.autograd.Function):
             if not last:
                 g_lps[i + 1] += r[4]
             if model.world_size > 1:                     # _AllReduce.backward (FastEGNN.py:19-21), one packed call
-                import torch.distributed as dist
-                dist.all_reduce(g_vsum, op=dist.ReduceOp.SUM, group=model.process_group)
+                model._sync_virtual(g_vsum, be, st.get("comm"))
             # ---- 2. node stage: (g_x', g_h', g_P', g_Q', g_Hn') -> g_h, g_x, g_agg_*, g_trans_v, parameter gradients -----
             with torch.enable_grad():
                 hl, xl = leaf(S["h"]), leaf(S["x4"][:, :3])

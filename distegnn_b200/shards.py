@@ -33,6 +33,38 @@ class CSRGraph:
     col: Tensor
     row: Optional[Tensor] = None
 
+    def __post_init__(self):
+        self._checked = None
+        for name, t in (("rowptr", self.rowptr), ("col", self.col), ("row", self.row)):
+            if t is None:
+                continue
+            if t.dtype != torch.int32 or t.dim() != 1:
+                raise ValueError(f"CSRGraph.{name} must be a 1-D int32 tensor (got {t.dtype}, shape {tuple(t.shape)}); "
+                                 "convert explicitly, e.g. torch.cumsum(...).to(torch.int32)")
+            if t.device != self.rowptr.device:
+                raise ValueError("CSRGraph tensors must live on one device")
+        if self.rowptr.numel() < 1:
+            raise ValueError("CSRGraph.rowptr must have N+1 >= 1 entries")
+        if self.row is not None and self.row.shape != self.col.shape:
+            raise ValueError("CSRGraph.row and .col must have the same length")
+
+    def validate(self, device=None) -> None:
+        """Content checks the kernels rely on (monotone rowptr ending at E, column ids in range); one host sync, done
+        once per CSRGraph object."""
+        if device is not None and self.rowptr.device != device:
+            raise ValueError(f"CSRGraph lives on {self.rowptr.device}, the node tensors on {device}")
+        if self._checked:
+            return
+        N, E = self.num_nodes, self.num_edges
+        ok = int(self.rowptr[0]) == 0 and int(self.rowptr[-1]) == E
+        if ok and N > 0:
+            ok = bool((self.rowptr[1:] >= self.rowptr[:-1]).all())
+        if ok and E > 0:
+            ok = N > 0 and int(self.col.min()) >= 0 and int(self.col.max()) < N
+        if not ok:
+            raise ValueError("CSRGraph is not a valid CSR: rowptr must be non-decreasing from 0 to E and col in [0, N)")
+        self._checked = True
+
     @property
     def num_nodes(self) -> int:
         return int(self.rowptr.shape[0]) - 1

@@ -13,11 +13,17 @@
  *   - every function returns 0 on success or a negative DISTEGNN_E* code; distegnn_last_error()
  *     returns a thread-local human-readable message for the last failure;
  *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer
- *     (inputs, outputs, workspaces); the library never allocates, frees or synchronises;
+ *     (inputs, outputs, workspaces); the library never allocates, frees or synchronises — the one
+ *     exception is the communicator (distegnn_comm_init / _destroy), which owns its peer-mapped segment;
  *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); the call returns as soon as
  *     the work is enqueued; it is safe inside CUDA-graph capture;
  *   - fp32 everywhere, node ids int32 after distegnn_build_csr (int64 at the reference boundary);
- *   - hidden width H is fixed at 64 (every shipped config: config/ *.yaml `hidden_nf: 64`).
+ *   - hidden width H is fixed at 64 (every shipped config: config/ *.yaml `hidden_nf: 64`);
+ *   - preconditions the kernels rely on and the host mirror validates (fast_egnn.py): data_batch is
+ *     non-decreasing with ids in [0, n_graphs) (FastEGNN.py:298 takes B from data_batch[-1]+1 and PyG batches are
+ *     sorted); edge ids lie in [0, n_nodes) (distegnn_build_csr returns DISTEGNN_EINVAL otherwise);
+ *   - cross-check twins of these entry points (fp32-FMA, 3xTF32, alternative tcgen05 flavours) live in
+ *     distegnn_b200_testing.h / libdistegnn_b200_testing.so and are not part of the product.
  *
  * Internal data layout (all row-major, contiguous)
  *   h      [N,64]   node features                x4     [N,4]  coordinates (xyz, w unused)
@@ -40,7 +46,7 @@
 extern "C" {
 #endif
 
-#define DISTEGNN_ABI_VERSION 1
+#define DISTEGNN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DISTEGNN_API __attribute__((visibility("default")))
@@ -66,6 +72,8 @@ enum {
 #define DISTEGNN_FLAG_NORMALIZE 1u  /* E_GCL_vel(normalize=True), FastEGNN.py:242-244                  */
 #define DISTEGNN_FLAG_LAST 2u       /* last layer: h'/Hv' are dead (FastEGNN.py:307) — skip them        */
 #define DISTEGNN_FLAG_INIT 4u       /* virtual_update before layer 0: no X / Hv update, only x̄, m_X, G */
+#define DISTEGNN_FLAG_ZERO_VSUM 8u  /* virtual_update: leave vsum zeroed (ready for the next layer's accumulation)  */
+#define DISTEGNN_FLAG_ZERO_AGG 16u  /* node_layer: leave agg_m / agg_x zeroed (ready for the next edge stage)       */
 
 DISTEGNN_API int distegnn_abi_version(void);
 DISTEGNN_API const char *distegnn_last_error(void);
@@ -124,11 +132,15 @@ DISTEGNN_API int distegnn_param_layout(int A, int C, int Na, int64_t *offsets_ho
  * edge_index[0] = aggregation destination, col = edge_index[1] = neighbour; FastEGNN.py:238,250) is
  * stably sorted by row into int32 CSR.  perm[e'] = original position of sorted edge e' (to permute
  * edge_attr).  Self loops, duplicate edges and isolated nodes are legal (equivariant_test.py:26-27).
+ * Ids outside [0, n_nodes) — on which the reference dies with a device-side index assert — are counted into the device
+ * counter *n_invalid (may be NULL) and clamped, so that nothing indexes out of bounds; the caller reads the counter once
+ * per graph (the build is cached) and raises.
  */
 DISTEGNN_API int distegnn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t *bytes_host);
 DISTEGNN_API int distegnn_build_csr(const int64_t *edge_index, int64_t n_nodes, int64_t n_edges,
                        int32_t *rowptr /*[N+1]*/, int32_t *row /*[E]*/, int32_t *col /*[E]*/,
-                       int32_t *perm /*[E]*/, void *workspace, int64_t workspace_bytes, void *stream);
+                       int32_t *perm /*[E]*/, void *workspace, int64_t workspace_bytes,
+                       int32_t *n_invalid /*[1], device, may be NULL*/, void *stream);
 
 /* dst[i,:] = src[perm[i],:] for i < n_rows, rows of `width` floats (edge_attr into CSR order). */
 DISTEGNN_API int distegnn_gather_rows(const float *src, const int32_t *perm, int64_t n_rows, int width, float *dst,
@@ -139,19 +151,14 @@ DISTEGNN_API int distegnn_gather_rows(const float *src, const int32_t *perm, int
  * node_loc [N,3] → x4, data_batch int64 → batch32, computes P/Q/Hn of layer 0 from `layer0_params`,
  * and accumulates Σx and the node count of every graph into vsum[:,0:4] (caller zeroes vsum).
  * emb_wt is embedding_in.weight^T [F][64], emb_b [64].
+ * data_batch must be non-decreasing with ids in [0, n_graphs): the per-graph reductions of every later stage rely on
+ * it.  Violations are counted into the device counter *n_invalid (may be NULL; the caller zeroes it) and the ids clamped.
  */
 DISTEGNN_API int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
                        const float *node_feat, const float *node_loc, const int64_t *data_batch,
                        const float *emb_wt, const float *emb_b, const float *layer0_params,
                        float *h, float *x4, int32_t *batch32, float *P, float *Q, float *Hn,
-                       float *vsum, void *stream);
-
-/* fp32-FMA twin of distegnn_embed_fwd (cross-check only). */
-DISTEGNN_API int distegnn_embed_fwd_simt(int64_t n_nodes, int n_graphs, int F, int A, int C, int Na,
-                                         const float *node_feat, const float *node_loc, const int64_t *data_batch,
-                                         const float *emb_wt, const float *emb_b, const float *layer0_params,
-                                         float *h, float *x4, int32_t *batch32, float *P, float *Q, float *Hn,
-                                         float *vsum, void *stream);
+                       float *vsum, int32_t *n_invalid, void *stream);
 
 /* ---- real↔real edge stage ------------------------------------------------------------------------
  * coord2radial + edge_model + the edge part of coord_model_vel + the edge part of node_model
@@ -179,13 +186,6 @@ DISTEGNN_API int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A
                                          const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
                                          float* g_x4, float* g_layer_params, void* stream);
 
-/* Same contract as distegnn_virtual_layer_fwd: the column-split flavour (two threads per row, 32 warps per SM;
- * csrc/virtual_layer_cs.cu) — measured 2 % slower than the production thread-per-row kernel; kept as a twin. */
-DISTEGNN_API int distegnn_virtual_layer_fwd_cs(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
-                                                const int32_t* batch32, const float* x4, const float* Hn,
-                                                const float* Xv, const float* G, const float* layer_params,
-                                                float* agg_v, float* trans_v, float* vsum, void* stream);
-
 /* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
  * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile; the six row-wise tile GEMMs run on tcgen05.
  * `weight_images` (96 KB, device): the stage's three 64x64 matrices and their transposes as fp16 hi/lo images in the
@@ -202,14 +202,6 @@ DISTEGNN_API int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A
                                             const float* g_agg_v, const float* g_trans_v, const float* g_vsum,
                                             float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
                                             void* stream);
-/* Same outputs with every tile GEMM as fp32 FMA on the CUDA cores (csrc/virtual_layer_bwd.cu; the first backward kernel,
- * kept as a twin).  wT = the matrices V_W2, V_WXV, V_WX TRANSPOSED as fp32 ([3][64][64], wT[m][n*64+k] = W_m[k*64+n]). */
-DISTEGNN_API int distegnn_virtual_layer_bwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
-                                                 const int32_t* batch32, const float* x4, const float* Hn, const float* Xv,
-                                                 const float* G, const float* layer_params, const float* wT,
-                                                 const float* g_agg_v, const float* g_trans_v, const float* g_vsum,
-                                                 float* g_Hn, float* g_xv, float* g_G, float* g_Xv, float* g_layer_params,
-                                                 void* stream);
 
 /* On-device radius graph: replaces the host-side `radius_graph(pos_i, r=radius, max_num_neighbors=N)`
  * + `edge_attr = |dx|` of the reference's partitioners (datasets/distribute_graphs.py:43-44; PyG / torch_cluster).
@@ -229,43 +221,6 @@ DISTEGNN_API int distegnn_radius_fill(int64_t n_nodes, const float* x4, const in
                                       const int32_t* dims_host, float radius, int loop, const int64_t* rowptr,
                                       int32_t* row, int32_t* col, float* dist, void* stream);
 
-/* Same contract as distegnn_edge_layer_bwd, every tile GEMM as fp32 FMA on the CUDA cores (csrc/edge_layer_bwd.cu): the
- * first backward kernel, kept as the twin of the tensor-core one for cross-checks. */
-DISTEGNN_API int distegnn_edge_layer_bwd_simt(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
-                                              const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
-                                              const float* x4, const float* P, const float* Q, const float* layer_params,
-                                              const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
-                                              float* g_x4, float* g_layer_params, void* stream);
-
-/* Same contract as distegnn_edge_layer_fwd: the thread-per-row tcgen05 kernel (16 warps per SM, 128 registers per
- * thread; csrc/edge_layer_tc16.cu).  The production symbol runs the column-split flavour (two threads per row, 32
- * warps per SM; csrc/edge_layer_cs.cu); this twin is kept for cross-checks and A/B timing. */
-DISTEGNN_API int distegnn_edge_layer_fwd_t16(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
-                                             const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
-                                             const float* x4, const float* P, const float* Q,
-                                             const float* layer_params, float* agg_m, float* agg_x, void* stream);
-
-/* Same contract as distegnn_edge_layer_fwd, computed with fp32 FMA on the CUDA cores (no tensor cores).
- * Kept as an independent implementation for cross-checks of the tcgen05 kernel at sizes the CPU oracle
- * cannot reach; not used by FastEGNN.forward. */
-DISTEGNN_API int distegnn_edge_layer_fwd_simt(int64_t n_nodes, int64_t n_edges, int A, int C, int Na,
-                                              unsigned flags, const int32_t *row, const int32_t *col,
-                                              const float *edge_attr_sorted, const float *x4, const float *P,
-                                              const float *Q, const float *layer_params, float *agg_m,
-                                              float *agg_x, void *stream);
-
-/* Same contract, tensor-core implementation with the 3xTF32 split (earlier production kernel; kept for A/B
- * measurements and as a third independent implementation in the cross-checks). */
-DISTEGNN_API int distegnn_edge_layer_fwd_tf32(int64_t n_nodes, int64_t n_edges, int A, int C, int Na,
-                                              unsigned flags, const int32_t *row, const int32_t *col,
-                                              const float *edge_attr_sorted, const float *x4, const float *P,
-                                              const float *Q, const float *layer_params, float *agg_m,
-                                              float *agg_x, void *stream);
-
-/* tcgen05 building-block self-test: D[128,64] = A[128,64]·W[64,64]^T on the tensor cores (variant 0:
- * 3xTF32 with A in TMEM, as the fused kernels use it; 2: A in shared memory; 4/6: single-pass TF32). */
-DISTEGNN_API int distegnn_selftest_umma(const float *A, const float *W, float *D, int variant, void *stream);
-
 /* ---- real↔virtual stage --------------------------------------------------------------------------
  * Virtual geometry + edge_mode_virtual + the virtual parts of coord_model_vel, coord_model_virtual,
  * node_model and node_model_virtual (FastEGNN.py:252-253, 154-163, 180, 191-193, 207, 220-223):
@@ -280,20 +235,6 @@ DISTEGNN_API int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A
                                const float *Xv, const float *G, const float *layer_params,
                                float *agg_v, float *trans_v /*[N,4]*/, float *vsum, void *stream);
 
-/* 3xTF32 tensor-core twin of distegnn_virtual_layer_fwd (cross-check / A-B timing only). */
-DISTEGNN_API int distegnn_virtual_layer_fwd_tf32(int64_t n_nodes, int n_graphs, int A, int C, int Na,
-                                                 unsigned flags, const int32_t *batch32, const float *x4,
-                                                 const float *Hn, const float *Xv, const float *G,
-                                                 const float *layer_params, float *agg_v, float *trans_v,
-                                                 float *vsum, void *stream);
-
-/* fp32-FMA twin of distegnn_virtual_layer_fwd (cross-check only). */
-DISTEGNN_API int distegnn_virtual_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na,
-                                                 unsigned flags, const int32_t *batch32, const float *x4,
-                                                 const float *Hn, const float *Xv, const float *G,
-                                                 const float *layer_params, float *agg_v, float *trans_v,
-                                                 float *vsum, void *stream);
-
 /* ---- node update ---------------------------------------------------------------------------------
  * The rest of coord_model_vel and node_model (FastEGNN.py:177-183, 203-217):
  *   x' = x + agg_x/max(deg,1) + trans_v + φ_v(h)·v
@@ -301,6 +242,8 @@ DISTEGNN_API int distegnn_virtual_layer_fwd_simt(int64_t n_nodes, int n_graphs, 
  * plus P/Q/Hn of the NEXT layer from next_layer_params, and vsum[b,0:4] += (x', 1).
  * With FLAG_LAST only x' is produced and additionally written as [N,3] to node_loc_out (the model
  * output); h_out/P/Q/Hn/next_layer_params may be null.  h_out may alias h, x4_out may alias x4.
+ * With FLAG_ZERO_AGG the kernel clears agg_m and agg_x after consuming them (they are written although declared
+ * const), so the caller needs no memset before the next edge stage.
  */
 DISTEGNN_API int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
                             const int32_t *rowptr, const int32_t *batch32, const float *h,
@@ -310,29 +253,53 @@ DISTEGNN_API int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, i
                             const float *next_layer_params, float *h_out, float *x4_out, float *P,
                             float *Q, float *Hn, float *node_loc_out, float *vsum, void *stream);
 
-/* fp32-FMA twin of distegnn_node_layer_fwd (cross-check only). */
-DISTEGNN_API int distegnn_node_layer_fwd_simt(int64_t n_nodes, int n_graphs, int A, int C, int Na, unsigned flags,
-                                              const int32_t *rowptr, const int32_t *batch32, const float *h,
-                                              const float *x4, const float *node_vel, const float *node_attr,
-                                              const float *agg_m, const float *agg_x, const float *agg_v,
-                                              const float *trans_v, const float *layer_params,
-                                              const float *next_layer_params, float *h_out, float *x4_out,
-                                              float *P, float *Q, float *Hn, float *node_loc_out, float *vsum,
-                                              void *stream);
+/* ---- virtual-node sync: packed SUM all-reduce over NVLink peer memory ------------------------------------------------
+ * Replaces weighted_average_reduce / _AllReduce (models/FastEGNN.py:10-43, 310-319; call sites :195-197, 225-227,
+ * 259-261 — six NCCL calls behind host syncs per layer) with ONE exchange of the packed statistics vsum [B,K] per layer.
+ * One process per GPU; every rank owns a segment of device memory that all peers map through CUDA IPC.  A call pushes the
+ * rank's values into every peer's segment, raises a per-slot flag, waits for the peers' flags and sums the `world`
+ * contributions in RANK ORDER, so the result is bit-identical on all ranks (the property the reference relies on NCCL
+ * for, FastEGNN.py:29-31) and independent of arrival order.  No host synchronisation, safe under CUDA-graph capture (the
+ * per-slot epoch lives in device memory).  All ranks must issue the same sequence of calls with the same sizes.
+ *
+ *   distegnn_comm_init     allocate + clear this rank's segment for calls of at most max_slots x slot_floats floats (for
+ *                          the model: max_slots >= B graphs, slot_floats >= K); returns the opaque communicator and this
+ *                          rank's IPC handle (distegnn_comm_handle_bytes() bytes, host memory).  Synchronises the device.
+ *   (caller)               all-gathers the handles over any host transport (the mirror uses torch.distributed)
+ *   distegnn_comm_connect  all_handles_host = world handles in rank order; maps the peers' segments
+ *   distegnn_allreduce_packed  in-place SUM of buf[0:count] over the ranks, enqueued on `stream`
+ *   distegnn_comm_status   *status_host != 0 if a wait timed out (a peer never arrived; default 10 s, see _set_timeout_ms)
+ *   distegnn_comm_destroy  unmap + free (the caller makes sure no rank still has calls in flight)
+ * The fused form — all-reduce of vsum[b,:] followed by the virtual-node update in the same kernel — is
+ * distegnn_virtual_update_fwd with a non-null `comm`.
+ */
+DISTEGNN_API int distegnn_comm_handle_bytes(void);
+DISTEGNN_API int distegnn_comm_init(int rank, int world, int max_slots, int slot_floats, void **comm_out,
+                                    void *handle_out_host);
+DISTEGNN_API int distegnn_comm_connect(void *comm, const void *all_handles_host);
+DISTEGNN_API int distegnn_comm_set_timeout_ms(void *comm, int64_t milliseconds);
+DISTEGNN_API int distegnn_comm_status(void *comm, int *status_host);
+DISTEGNN_API int distegnn_comm_destroy(void *comm);
+DISTEGNN_API int distegnn_allreduce_packed(void *comm, float *buf, int64_t count, void *stream);
 
-/* ---- virtual-node update (after the all-reduce of vsum) ------------------------------------------
+/* ---- virtual-node update, fused with the all-reduce of vsum ---------------------------------------------------------
  * The global halves of coord_model_virtual / node_model_virtual and the next layer's m_X
  * (FastEGNN.py:199, 229-233, 258-264) from the *summed* statistics (weighted_average_reduce,
- * FastEGNN.py:310-319, is Σ_r n_r·mean_r / Σ_r n_r = Σ_r sum_r / Σ_r n_r):
+ * FastEGNN.py:310-319, is Σ_r n_r·mean_r / Σ_r n_r = Σ_r sum_r / Σ_r n_r).  One CTA per graph:
+ *   [comm != NULL]  vsum[b,:] := Σ over the partitions (the exchange described above, slot = graph)
  *   n = max(vsum[b,3],1);  Xv += vsum[b,4:4+3C]/n;  Hv += MLP_hv([Hv; vsum[b,4+3C:]/n])
  *   x̄ = vsum[b,0:3]/n;  m_X = (Xv−x̄)ᵀ(Xv−x̄);  G_next = W1v_V·Hv + W1v_M·m_X + b1v (next layer's)
- * FLAG_INIT: skip the Xv/Hv updates (before layer 0).  FLAG_LAST: only Xv is updated.
+ * FLAG_INIT: skip the Xv/Hv updates (before layer 0); if init_loc_mean [B,3] / init_hv0 [C,64] are given, Xv / Hv are
+ * first initialised from them (FastEGNN.py:299-300) instead of being read.  FLAG_LAST: only Xv is updated.
+ * FLAG_ZERO_VSUM: vsum is left zeroed for the next layer's accumulation; otherwise it holds the summed statistics on
+ * return (the training path keeps them for the backward pass).
  * layer_params: this layer's block (node_mlp_virtual); next_layer_params: the block whose virtual MLP
  * consumes G (null with FLAG_LAST).  With FLAG_INIT pass layer 0's block as next_layer_params.
  */
-DISTEGNN_API int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na, unsigned flags, const float *vsum,
+DISTEGNN_API int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na, unsigned flags, float *vsum,
                                 float *Xv, float *Hv, const float *layer_params,
-                                const float *next_layer_params, float *G, void *stream);
+                                const float *next_layer_params, float *G, const float *init_loc_mean,
+                                const float *init_hv0, void *comm, void *stream);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,14 @@ def main():
     if args.virtual_channels is not None:
         cfg["model"]["virtual_channels"] = args.virtual_channels
 
+    # options of the reference CLI that belong to its data pipeline / epoch loop (out of scope here): say so, loudly
+    ignored = [n for n, v in (("--wandb", args.wandb), ("--early_stop", args.early_stop), ("--cutoff_rate", args.cutoff_rate),
+                              ("--outer_radius", args.outer_radius)) if v]
+    if ignored and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        print(f"WARNING: {', '.join(ignored)} accepted for CLI compatibility but NOT used: logging, early stopping and "
+              "the cutoff / outer-radius edge pruning live in the reference's data pipeline and epoch loop "
+              "(utils/train.py, datasets/process_dataset.py), which this entry point does not replace", flush=True)
+
     assert torch.cuda.is_available(), "distegnn_b200 needs CUDA devices (there is no CPU path)"
     distributed = "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -184,7 +192,8 @@ def train_steps(args, cfg, model, inp, forward, world_size, local_rank, distribu
     tc = cfg.get("train", {}) or {}
     mmd = tc.get("mmd", {}) or {}
     sigma, mmd_w, samples = float(mmd.get("sigma", 3)), float(mmd.get("weight", 0.01)), int(mmd.get("samples", 50))
-    lr = args.lr if args.lr is not None else float(tc.get("lr", 5e-4))
+    # the reference's YAML key is `learning_rate` (config/largefluid_distegnn.yaml:26); `--lr` overrides it (main.py:118-119)
+    lr = args.lr if args.lr is not None else float(tc.get("learning_rate", tc.get("lr", 5e-4)))
     C = cfg["model"]["virtual_channels"]
     model.train()
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=float(tc.get("weight_decay", 1e-12)))

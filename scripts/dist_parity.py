@@ -1,14 +1,14 @@
 """Multi-GPU parity: run under torchrun with N ranks (one per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
-        scripts/dist_parity.py [--workload fluid113k] [--nodes 113140] [--split-mode random|kmeans]
+        scripts/dist_parity.py [--workload fluid113k] [--nodes 113140] [--split-mode random|kmeans] [--grads] [--cuda-graph]
 
-Every rank builds the same seeded graph, takes its partition (distribute_graphs.py semantics restated in
-distegnn_b200/synth.py), runs FastEGNN(world_size=N) through the CUDA path with the packed NCCL all-reduce, and
-rank 0 compares all ranks' outputs with the oracle evaluated on the P partitions in one process
-(== the reference's world_size=N branch, see tests/test_oracle_golden.py).
+Thin command-line wrapper of oracle/dist_check.py (the checker bench.py also runs before its timed region): every rank
+runs its partition through the CUDA path with the real cross-rank exchange, rank 0 compares all ranks' outputs with the
+partitioned float64 oracle and prints one JSON line + `DIST_PARITY PASS|FAIL`.
 """
 import argparse
+import json
 import os
 import sys
 
@@ -17,7 +17,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from distegnn_b200 import FastEGNN, synth  # noqa: E402
 
 
 def main():
@@ -25,102 +24,24 @@ def main():
     ap.add_argument("--workload", default="fluid113k")
     ap.add_argument("--nodes", type=int, default=None)
     ap.add_argument("--split-mode", default="random")
-    ap.add_argument("--grads", action="store_true", help="also check the training path: parameter gradients of "
-                    "sum_r <out_r, cot_r> + <X, cot_X>, summed over the ranks, against float64 autograd through the "
-                    "partitioned oracle (use a small --nodes: the oracle runs on the host)")
+    ap.add_argument("--grads", action="store_true", help="also check the training path (use a small --nodes: the "
+                    "oracle's float64 autograd runs on the host)")
+    ap.add_argument("--cuda-graph", action="store_true", help="run the forward as a captured CUDA graph (replayed once)")
     args = ap.parse_args()
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    w = synth.WORKLOADS[args.workload]
-    parts = synth.make_partitions(w, world_size=world, split_mode=args.split_mode, seed=11, n_nodes=args.nodes)
-    from oracle import fastegnn_oracle as orc
-    sd = orc.init_state_dict(w.node_feat_nf, w.node_attr_nf, w.edge_attr_nf, 64, w.virtual_channels, 4, seed=3,
-                             coord_gain=0.05)
-    m = FastEGNN(node_feat_nf=w.node_feat_nf, node_attr_nf=w.node_attr_nf, edge_attr_nf=w.edge_attr_nf,
-                 hidden_nf=64, virtual_channels=w.virtual_channels, world_size=world, n_layers=4,
-                 normalize=w.normalize)
-    m.load_state_dict(sd)
-    m = m.to(dev).eval()
-    inp = {k: (v.to(dev) if v is not None else None) for k, v in parts[rank].items()}
-    with torch.no_grad():
-        out, X = m(**inp)
-    torch.cuda.synchronize()
-    sizes = [p["node_loc"].shape[0] for p in parts]
-    gathered = [torch.empty(n, 3, device=dev) for n in sizes]
-    # all_gather with uneven sizes: pad to max
-    mx = max(sizes)
-    pad = torch.zeros(mx, 3, device=dev)
-    pad[:out.shape[0]] = out
-    bufs = [torch.empty(mx, 3, device=dev) for _ in range(world)]
-    dist.all_gather(bufs, pad)
-    Xs = [torch.empty_like(X) for _ in range(world)]
-    dist.all_gather(Xs, X)
-    ok = True
+    from oracle import dist_check
+    res = dist_check.check_case(args.workload, args.nodes, args.split_mode, dev, grads=args.grads,
+                                cuda_graph=args.cuda_graph)
     if rank == 0:
-        sd64 = {k: v.double() for k, v in sd.items()}
-        p64 = [{k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in p.items()}
-               for p in parts]
-        refs, refX = orc.forward_partitions(sd64, [{k: v for k, v in p.items() if k != "loc_mean"} for p in p64],
-                                            p64[0]["loc_mean"], normalize=w.normalize)
-        for r in range(world):
-            o = bufs[r][:sizes[r]].cpu().double()
-            err = float((o - refs[r]).abs().max())
-            disp = float((refs[r] - p64[r]["node_loc"]).abs().max())
-            ex = float((Xs[r].cpu().double() - refX).abs().max())
-            same = bool((Xs[r] == Xs[0]).all())
-            print(f"rank {r}: N={sizes[r]} E={parts[r]['edge_index'].shape[1]} max|out-ref64|={err:.3e} "
-                  f"rel-disp={err / disp:.3e} virtual={ex:.3e} virtual-bit-identical-to-rank0={same}", flush=True)
-            ok &= err <= 1e-5 * max(1.0, float(refs[r].abs().max())) and err / disp <= 1e-4 and ex <= 1e-5 and same
-        print("DIST_PARITY", "PASS" if ok else "FAIL", f"world={world} split={args.split_mode} {args.workload}",
-              flush=True)
-    if args.grads:
-        g = torch.Generator().manual_seed(17)
-        cots = [torch.randn(n, 3, generator=g) for n in sizes]
-        cotX = torch.randn(X.shape, generator=g)
-        m.train()
-        out, X = m(**inp)
-        ((out * cots[rank].to(dev)).sum() + (X * cotX.to(dev)).sum()).backward()
-        names = [k for k, _ in m.named_parameters()]
-        flat = torch.cat([(p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1) for _, p_ in m.named_parameters()])
-        dist.all_reduce(flat)                                    # Σ over ranks of each rank's parameter gradient
-        if rank == 0:
-            sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
-            p64 = [{k: (v.double() if (v is not None and v.is_floating_point()) else v) for k, v in p.items()}
-                   for p in parts]
-            refs, refX = orc.forward_partitions(sd64, [{k: v for k, v in p.items() if k != "loc_mean"} for p in p64],
-                                                p64[0]["loc_mean"], normalize=w.normalize)
-            loss = sum((refs[r] * cots[r].double()).sum() for r in range(world)) + world * (refX * cotX.double()).sum()
-            rg = torch.autograd.grad(loss, [sd64[k] for k in names], allow_unused=True)
-            # the same in float32: the reference arithmetic's own rounding noise on these (heavily cancelling) sums sets the
-            # scale of the gate — measured on this 8-partition case: 9e-4 on gcl_3.coord_mlp_v_virtual.0.bias
-            sd32 = {k: v.float().requires_grad_(True) for k, v in sd.items()}
-            r32, X32 = orc.forward_partitions(sd32, [{k: v for k, v in p.items() if k != "loc_mean"} for p in parts],
-                                              parts[0]["loc_mean"], normalize=w.normalize)
-            l32 = sum((r32[r] * cots[r]).sum() for r in range(world)) + world * (X32 * cotX).sum()
-            rg32 = torch.autograd.grad(l32, [sd32[k] for k in names], allow_unused=True)
-            off, worst, wk, wtol = 0, 0.0, "", 0.0
-            for k, r_, q_ in zip(names, rg, rg32):
-                n = sd[k].numel()
-                mine = flat[off:off + n].cpu().double().reshape(sd[k].shape)
-                off += n
-                if r_ is None or float(r_.abs().max()) == 0.0:
-                    ok &= float(mine.abs().max()) == 0.0
-                    continue
-                den = float(r_.abs().max())
-                e = float((mine - r_).abs().max() / den)
-                noise = float((q_.double() - r_).abs().max() / den)
-                tol = max(2e-4, 3.0 * noise)
-                ok &= e <= tol
-                if e / tol > (worst / wtol if wtol else 0.0):
-                    worst, wk, wtol = e, k, tol
-            print(f"gradients summed over {world} ranks vs float64 autograd through the partitioned oracle: tightest "
-                  f"{wk} err {worst:.3e} (gate {wtol:.3e} = max(2e-4, 3 x the oracle's own fp32-vs-fp64 difference))", flush=True)
-            print("DIST_GRAD_PARITY", "PASS" if ok else "FAIL", flush=True)
+        print(json.dumps(res), flush=True)
+        print("DIST_PARITY", "PASS" if res["pass"] else "FAIL",
+              f"world={res['world']} split={args.split_mode} {args.workload}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    if rank == 0 and not ok:
+    if not res["pass"]:
         sys.exit(1)
 
 

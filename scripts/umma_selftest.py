@@ -1,7 +1,7 @@
 import ctypes, torch, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from distegnn_b200 import _lib
-lib = _lib.load()
+from tests.twin_backend import load_testing
+lib = load_testing()
 fn = lib.distegnn_selftest_umma
 torch.manual_seed(0)
 dev = torch.device('cuda:0')

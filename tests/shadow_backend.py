@@ -40,7 +40,9 @@ class ShadowBackend:
     def __init__(self):
         self.launches = 0
 
-    def build_csr(self, edge_index, n_nodes):
+    def build_csr(self, edge_index, n_nodes, validate=True):
+        if validate and edge_index.numel() and (int(edge_index.min()) < 0 or int(edge_index.max()) >= n_nodes):
+            raise ValueError(f"edge_index has edge(s) with a node id outside [0, {n_nodes})")
         row64 = edge_index[0]
         perm = torch.argsort(row64, stable=True)
         row = row64[perm].to(torch.int32)
@@ -54,8 +56,13 @@ class ShadowBackend:
         return src[perm.long()].contiguous()
 
     def embed(self, dims, node_feat, node_loc, data_batch, emb_wt, emb_b, layer0, h, x4, batch32, P, Q,
-              Hn, vsum):
+              Hn, vsum, n_invalid=None):
         N, B, Fn, A, C, Na = dims
+        if n_invalid is not None and N:
+            bad = (data_batch < 0) | (data_batch >= B)
+            bad[1:] |= data_batch[1:] < data_batch[:-1]
+            n_invalid += int(bad.sum())
+            data_batch = data_batch.clamp(0, B - 1)
         h.copy_(node_feat @ emb_wt + emb_b)
         x4.zero_()
         x4[:, :3] = node_loc
@@ -124,10 +131,27 @@ class ShadowBackend:
             loc_out.copy_(xn)
         vsum[:, 0:3].index_add_(0, b, xn)
         vsum[:, 3].index_add_(0, b, torch.ones(N, dtype=vsum.dtype, device=vsum.device))
+        if flags & _lib.FLAG_ZERO_AGG:
+            agg_x.zero_()
+            if agg_m is not None:
+                agg_m.zero_()
 
-    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G):
+    def allreduce_packed(self, comm, buf):
+        comm.all_reduce(buf)
+
+    def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G, init_loc_mean=None, init_hv0=None, comm=None):
         B, A, C, Na = dims
         init, last = bool(flags & _lib.FLAG_INIT), bool(flags & _lib.FLAG_LAST)
+        if comm is not None:
+            comm.all_reduce(vsum)
+        vsum_live = vsum
+        vsum = vsum.clone()
+        if flags & _lib.FLAG_ZERO_VSUM:
+            vsum_live.zero_()
+        if init and init_loc_mean is not None:
+            Xv.copy_(init_loc_mean.unsqueeze(-1).expand(B, 3, C))
+        if init and init_hv0 is not None and Hv is not None:
+            Hv.copy_(init_hv0.unsqueeze(0).expand(B, C, H))
         n = vsum[:, 3].clamp(min=1)
         if not init:
             Xv += vsum[:, 4:4 + 3 * C].reshape(B, 3, C) / n.view(B, 1, 1)

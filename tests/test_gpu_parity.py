@@ -7,6 +7,8 @@
 Tolerances (fp32 path): |out − ref64| ≤ 1e-5·max(1,|out|), relative displacement error
 ≤ 1e-4, equivariance residual ≤ 1e-4 (the reference's own gate, equivariant_test.py:62).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -57,14 +59,14 @@ def check_close(out, X, ref, refX, pos, what=""):
 
 def test_library_loaded_and_abi():
     lib = _lib.load()
-    assert lib.distegnn_abi_version() == 1
+    assert lib.distegnn_abi_version() == 2
 
 
 def test_tcgen05_building_block():
     """D = A·Wᵀ on the tensor cores with the 3xTF32 split must be fp32-accurate (and plain TF32 must not
     be — that is why the split exists)."""
-    import ctypes
-    lib = _lib.load()
+    from tests.twin_backend import load_testing
+    lib = load_testing()
     g = torch.Generator().manual_seed(0)
     A = torch.randn(128, 64, generator=g).to(dev())
     W = (torch.randn(64, 64, generator=g) / 8).to(dev())
@@ -85,8 +87,8 @@ def test_tcgen05_building_block():
 def test_edge_kernel_tensor_core_vs_fma_twin():
     """The tcgen05 edge kernel against its independent fp32-FMA implementation on a 300k-node graph
     (both normalisation modes, with and without the Σm output)."""
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     w = synth.WORKLOADS["synth1m"]
     inp = to_dev(synth.make_partitions(w, n_nodes=300_000, seed=7)[0])
     sd = orc.init_state_dict(3, 2, 2, 64, 8, 1, seed=2, coord_gain=1.0)
@@ -118,8 +120,8 @@ def test_edge_kernel_tensor_core_vs_fma_twin():
 def test_edge_kernel_fp16_range_rescue():
     """Activations far outside the fp16 range (up to ~1e7) must still come out fp32-accurate: rows that
     overflow are re-encoded with a per-row power-of-two scale inside the kernel."""
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     w = synth.WORKLOADS["water3d_10k"]
     inp = to_dev(synth.make_partitions(w, n_nodes=20_000, seed=9)[0])
     sd = orc.init_state_dict(2, 0, 2, 64, 3, 1, seed=2, coord_gain=1.0)
@@ -171,8 +173,8 @@ def test_edge_kernel_silu_batch_guard():
     silu4p).  Pre-activations around −20 … −45 make that product leave the fp32 range while every single d stays
     finite; the stage-level guard must then redo the rows with per-element reciprocals.  Rows with such
     pre-activations sit next to ordinary ones in the same warp / quad."""
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     w = synth.WORKLOADS["water3d_10k"]
     inp = to_dev(synth.make_partitions(w, n_nodes=20_000, seed=11)[0])
     sd = orc.init_state_dict(2, 0, 2, 64, 3, 1, seed=3, coord_gain=1.0)
@@ -213,8 +215,8 @@ def test_edge_kernel_silu_batch_guard():
 def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
     """tcgen05 virtual-stage kernel against its fp32-FMA twin (single graph and a batch whose tiles
     straddle graph boundaries; C = 8 / 5 / 3 exercise full and ragged row tiles)."""
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     N = 100_003
     g = torch.Generator().manual_seed(C)
     sd = orc.init_state_dict(3, 0, 2, 64, C, 1, seed=5, coord_gain=1.0)
@@ -246,8 +248,8 @@ def test_virtual_kernel_tensor_core_vs_fma_twin(C, B):
 
 @pytest.mark.parametrize("F,B", [(3, 1), (1, 11), (16, 2)])
 def test_embed_kernel_tensor_core_vs_fma_twin(F, B):
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     N, C = 50_003, 3
     d = dev()
     g = torch.Generator().manual_seed(F)
@@ -274,8 +276,8 @@ def test_embed_kernel_tensor_core_vs_fma_twin(F, B):
 def test_node_kernel_tensor_core_vs_fma_twin(Na, B, big):
     """tcgen05 node-update kernel against its fp32-FMA twin: single graph / batch with straddling tiles, with and
     without node attributes, last-layer mode, and (big) features far outside the fp16 range."""
-    from distegnn_b200.backend import cuda_backend
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     N, C = 70_001, 5
     d = dev()
     g = torch.Generator().manual_seed(Na + B)
@@ -351,20 +353,38 @@ def _stage_inputs(kw, sd, inp):
 
 @pytest.mark.parametrize("name", SINGLE_CASES)
 def test_per_layer_trace_against_reference(name):
-    """h / x after every layer, not just the final coordinates (parity is deceptively easy at init)."""
+    """h, x, Hv and X after EVERY layer of the CUDA path against the traces the unmodified reference produced
+    (forward hooks in oracle/make_golden.py) — not just the final coordinates: parity is deceptively easy at init,
+    coordinates barely see a wrong edge MLP.  The training-path forward keeps each layer's inputs, i.e. the
+    previous layer's outputs; one extra (dummy) layer makes the last real layer's h'/Hv' live (they are dead code
+    otherwise, FastEGNN.py:307)."""
     z, kw, sd = load_golden(name)
     inp = golden_inputs(z)
-    ref_h, ref_x = golden_trace(z, "h"), golden_trace(z, "x")
-    for L in range(1, kw["n_layers"] + 1):
-        # a model truncated to L layers: its last layer must reproduce x_L; use L+1 layers to read h_L
-        sub = {k: v for k, v in sd.items() if not k.startswith("gcl_") or int(k.split(".")[0][4:]) < L}
-        kwL = dict(kw, n_layers=L)
-        m = cuda_model(kwL, sub)
-        with torch.no_grad():
-            out, _ = m(**to_dev(inp))
-        e = max_abs(out.cpu(), ref_x[L - 1])
-        print(f"{name} layer {L}: x err {e:.3e}")
-        assert e <= 2e-5 * max(1.0, float(ref_x[L - 1].abs().max()))
+    L = kw["n_layers"]
+    ref = {k: golden_trace(z, k) for k in ("h", "x", "Hv", "X")}
+    assert all(len(v) == L for v in ref.values())
+    sdx = dict(sd)
+    for k, v in sd.items():
+        if k.startswith(f"gcl_{L - 1}."):
+            sdx[k.replace(f"gcl_{L - 1}.", f"gcl_{L}.")] = v.clone()
+    m = cuda_model(dict(kw, n_layers=L + 1), sdx).train()
+    kept = []
+    m._keep_state = kept
+    m(**to_dev(inp))
+    torch.cuda.synchronize()
+    layers = kept[0]["layers"]
+    assert len(layers) == L + 1
+    worst = {}
+    for l in range(L):
+        nxt = layers[l + 1]                      # inputs of layer l+1 == outputs of layer l
+        got = dict(h=nxt["h"], x=nxt["x4"][:, :3], Hv=nxt["Hv"].transpose(1, 2), X=nxt["Xv"])
+        for k, g in got.items():
+            r = ref[k][l]
+            e = max_abs(g.cpu(), r) / max(1.0, float(r.abs().max()))
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e <= 2e-5, f"{name} layer {l} {k}: rel err {e:.3e}"
+    print(f"{name}: per-layer trace vs reference, worst relative error " +
+          ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
 
 
 def _kernel_vs_shadow(name):
@@ -621,9 +641,9 @@ def _rel(a, b):
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags,A", [(0, 2), (_lib.FLAG_NORMALIZE, 2), (_lib.FLAG_LAST, 2), (0, 0)])
 def test_edge_stage_backward(flags, A):
-    from distegnn_b200.backend import cuda_backend
     from tests import shadow_autograd as sa
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     w = synth.WORKLOADS["water3d_10k"]
     inp = to_dev(synth.make_partitions(w, n_nodes=6_000, seed=21)[0])
     C, Na = 3, 0
@@ -665,9 +685,9 @@ def test_edge_stage_backward(flags, A):
 @pytest.mark.gpu
 @pytest.mark.parametrize("C,B,last", [(8, 1, False), (3, 5, False), (5, 1, True), (16, 2, False), (1, 3, False)])
 def test_virtual_stage_backward(C, B, last):
-    from distegnn_b200.backend import cuda_backend
     from tests import shadow_autograd as sa
-    be = cuda_backend()
+    from tests.twin_backend import twin_backend
+    be = twin_backend()
     A, Na, N = 2, 0, 5_003
     sd = orc.init_state_dict(2, Na, A, 64, C, 1, seed=8, coord_gain=1.0)
     m = cuda_model(dict(node_feat_nf=2, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=1), sd)
@@ -935,3 +955,180 @@ def test_shard_input_path_matches_edge_index_path(tmp_path):
     assert max_abs(out_a, out_b) <= 2e-6 and max_abs(X_a, X_b) <= 2e-6
     print(f"shard: {sh.nbytes() / 2**20:.1f} MiB on the wire vs "
           f"{sum(v.numel() * v.element_size() for v in host.values() if v is not None) / 2**20:.1f} MiB for the tensors of the reference API")
+
+
+# ---- virtual-node sync: the library's own exchange (csrc/comm.cuh) -------------------------------------------------------
+def _solo_comm(max_slots, slot_floats):
+    """A communicator of world size 1 on this process' GPU: the same kernel path (push, flag, wait, ordered reduce),
+    with the only 'peer' being the rank itself — what a single-GPU box can exercise of the collective."""
+    import ctypes as C
+    lib = _lib.load()
+    nb = lib.distegnn_comm_handle_bytes()
+    mine = (C.c_ubyte * nb)()
+    h = C.c_void_p()
+    _lib.check(lib.distegnn_comm_init(0, 1, max_slots, slot_floats, C.byref(h), mine), "comm_init")
+    _lib.check(lib.distegnn_comm_connect(h, mine), "comm_connect")
+
+    class Solo:
+        handle = h
+
+        @staticmethod
+        def status():
+            v = C.c_int(0)
+            _lib.check(lib.distegnn_comm_status(h, C.byref(v)), "comm_status")
+            return v.value
+
+        @staticmethod
+        def destroy():
+            lib.distegnn_comm_destroy(h)
+    return Solo
+
+
+@pytest.mark.gpu
+def test_packed_allreduce_single_rank_is_identity_and_replayable():
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    comm = _solo_comm(max_slots=5, slot_floats=540)
+    try:
+        g = torch.Generator().manual_seed(0)
+        for n in (1, 540, 541, 5 * 540):                         # partial slot, one slot, two slots, full capacity
+            buf = torch.randn(n, generator=g).to(dev())
+            want = buf.clone()
+            for _ in range(3):                                   # epochs advance, parity double-buffer flips
+                be.allreduce_packed(comm, buf)
+            torch.cuda.synchronize()
+            assert torch.equal(buf, want)
+        with pytest.raises(ValueError, match="capacity"):
+            be.allreduce_packed(comm, torch.zeros(5 * 540 + 1, device=dev()))
+        # under CUDA-graph capture: the per-slot epoch lives in device memory, so replays stay consistent
+        buf = torch.randn(700, generator=g).to(dev())
+        want = buf.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            be.allreduce_packed(comm, buf)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            be.allreduce_packed(comm, buf)
+        for _ in range(4):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(buf, want) and comm.status() == 0
+    finally:
+        torch.cuda.synchronize()
+        comm.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,B", [(8, 1), (5, 3), (16, 2)])
+def test_fused_sync_update_equals_plain_update(C, B):
+    """virtual_update with a communicator (all-reduce inside the kernel) == without, on one rank; FLAG_ZERO_VSUM clears the
+    statistics, without it the (summed) statistics stay in vsum; the INIT flavour initialises Xv / Hv itself."""
+    from distegnn_b200.backend import cuda_backend
+    be = cuda_backend()
+    A, Na = 2, 0
+    K = 4 + 3 * C + 64 * C
+    sd = orc.init_state_dict(2, Na, A, 64, C, 2, seed=4, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=2), sd)
+    pk = m._packed_params(dev())
+    g = torch.Generator().manual_seed(1)
+    vs = torch.randn(B, K, generator=g).to(dev())
+    vs[:, 3] = torch.tensor([1000.0 + 7 * b for b in range(B)])
+    loc_mean = torch.randn(B, 3, generator=g).to(dev())
+    comm = _solo_comm(max_slots=B, slot_floats=K)
+    try:
+        res = {}
+        for tag, cm, zero in (("plain", None, 0), ("fused", comm, 0), ("fused_zero", comm, _lib.FLAG_ZERO_VSUM)):
+            v = vs.clone()
+            Xv, Hv, G = (torch.full((B, 3, C), 7.0, device=dev()), torch.full((B, C, 64), 7.0, device=dev()),
+                         torch.empty(B, C, 64, device=dev()))
+            be.virtual_update((B, A, C, Na), _lib.FLAG_INIT | zero, v, Xv, Hv, None, pk["layers"][0], G,
+                              loc_mean, pk["hv0"], cm)
+            v0 = v.clone()
+            v.copy_(vs)
+            be.virtual_update((B, A, C, Na), zero, v, Xv, Hv, pk["layers"][0], pk["layers"][1], G, comm=cm)
+            torch.cuda.synchronize()
+            res[tag] = (Xv, Hv, G, v0, v.clone())
+        for tag in ("fused", "fused_zero"):
+            for a, b in zip(res[tag][:3], res["plain"][:3]):
+                assert torch.equal(a, b), tag
+        assert torch.equal(res["fused"][4], vs) and torch.equal(res["plain"][4], vs)
+        assert float(res["fused_zero"][3].abs().max()) == 0.0 and float(res["fused_zero"][4].abs().max()) == 0.0
+        # the INIT flavour wrote Xv = loc_mean per channel and Hv = virtual_node_feat before updating
+        Xv0 = torch.empty(B, 3, C, device=dev())
+        Hv0 = torch.empty(B, C, 64, device=dev())
+        G0 = torch.empty(B, C, 64, device=dev())
+        be.virtual_update((B, A, C, Na), _lib.FLAG_INIT, vs.clone(), Xv0, Hv0, None, pk["layers"][0], G0, loc_mean, pk["hv0"])
+        torch.cuda.synchronize()
+        assert torch.equal(Xv0, loc_mean.unsqueeze(-1).expand(B, 3, C)) and torch.equal(Hv0, pk["hv0"].expand(B, C, 64))
+        assert comm.status() == 0
+    finally:
+        torch.cuda.synchronize()
+        comm.destroy()
+
+
+@pytest.mark.gpu
+def test_forward_leaves_accumulators_clean_and_launches_only_kernels():
+    """No memset / copy launches in steady state: the consumers clear vsum / agg_m / agg_x (FLAG_ZERO_*), so after every
+    forward the workspace accumulators are zero again and back-to-back forwards agree; a forward is 2 + 4L launches."""
+    from distegnn_b200.backend import cuda_backend
+    w = synth.WORKLOADS["fluid113k"]
+    inp = to_dev(synth.make_partitions(w, n_nodes=20_011, seed=5)[0])
+    sd = orc.init_state_dict(3, 2, 2, 64, 5, 4, seed=2, coord_gain=0.05)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=2, edge_attr_nf=2, virtual_channels=5, n_layers=4), sd)
+    be = cuda_backend()
+    with torch.no_grad():
+        o1, X1 = m(**inp)
+        n0 = be.launches
+        o2, X2 = m(**inp)
+        assert be.launches - n0 == 2 + 4 * 4
+        torch.cuda.synchronize()
+        ws = next(iter(m._workspaces.values()))
+        for k in ("vsum", "agg_m", "agg_x"):
+            assert float(ws[k].abs().max()) == 0.0, k
+        assert not ws["dirty"]
+        assert max_abs(o1, o2) <= 2e-6 and max_abs(X1, X2) <= 2e-6
+        assert o1.data_ptr() != o2.data_ptr()                  # results are fresh tensors, not workspace views
+    ref, refX = oracle64(sd, {k: (v.cpu() if v is not None else None) for k, v in inp.items()}, False)
+    check_close(o2, X2, ref, refX, inp["node_loc"].cpu(), "self-cleaning workspace")
+
+
+@pytest.mark.gpu
+def test_validation_on_device():
+    """Bad data_batch / edge ids are caught by the device-side counters (embed / CSR build) and raise."""
+    inp = to_dev(synth.make_partitions(synth.WORKLOADS["water3d_10k"], n_nodes=3_000, seed=9)[0])
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 2, seed=0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=2), sd)
+    with torch.no_grad():
+        good, _ = m(**inp)
+        b = inp["data_batch"].clone()
+        b[100] = 1
+        with pytest.raises(ValueError, match="data_batch"):
+            m(**dict(inp, data_batch=b))
+        ei = inp["edge_index"].clone()
+        ei[0, 5] = inp["node_loc"].shape[0]
+        with pytest.raises(ValueError, match="edge_index"):
+            m(**dict(inp, edge_index=ei))
+        again, _ = m(**inp)                                      # dirty workspace after the failures is re-zeroed
+        assert max_abs(good, again) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split_mode,extra", [("random", ["--cuda-graph", "--grads", "--nodes", "12000"]),
+                                               ("kmeans", ["--nodes", "30000"])])
+def test_multi_gpu_parity_under_torchrun(split_mode, extra):
+    """2 ranks (2 GPUs) under torchrun: every rank's CUDA path + the peer-memory exchange vs the partitioned float64
+    oracle (oracle/dist_check.py).  Skipped on a single-GPU box — bench.py runs the same check under the driver's
+    multi-GPU launches and puts it into its JSON line (`dist_parity`)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dist_parity.py"), "--workload",
+           "fluid113k", "--split-mode", split_mode, *extra]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    print(p.stdout[-3000:], p.stderr[-1500:])
+    assert p.returncode == 0 and "DIST_PARITY PASS" in p.stdout

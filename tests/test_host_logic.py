@@ -150,3 +150,72 @@ def test_empty_edge_set():
         out, X = m(**inp)
         ref, refX = orc.forward(sd, **inp)
     assert max_abs(out, ref) <= 1e-5 and max_abs(X, refX) <= 1e-5
+
+
+# ---- input validation: the fused reductions rely on preconditions the reference's scatters do not need ----
+def _tiny_inputs(n=12, e=40, B=2, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    batch = torch.sort(torch.randint(0, B, (n,), generator=g)).values
+    batch[0], batch[-1] = 0, B - 1
+    return dict(node_feat=torch.randn(n, 2, generator=g), node_loc=torch.randn(n, 3, generator=g),
+                node_vel=torch.randn(n, 3, generator=g), loc_mean=torch.zeros(B, 3),
+                edge_index=torch.randint(0, n, (2, e), generator=g), data_batch=batch,
+                edge_attr=torch.rand(e, 2, generator=g), node_attr=None)
+
+
+def _tiny_model():
+    sd = orc.init_state_dict(2, 0, 2, 64, 3, 2, seed=0)
+    return make_model(dict(node_feat_nf=2, node_attr_nf=0, edge_attr_nf=2, virtual_channels=3, n_layers=2), sd)
+
+
+def test_unsorted_or_out_of_range_data_batch_raises():
+    m = _tiny_model()
+    inp = _tiny_inputs()
+    with torch.no_grad():
+        m(**inp)                                                  # valid input passes (and is remembered as validated)
+        bad = dict(inp, data_batch=inp["data_batch"].flip(0).contiguous())
+        with pytest.raises(ValueError, match="data_batch"):
+            m(**bad)
+        bad = dict(inp, data_batch=inp["data_batch"] + 1)         # id == B: out of range (B = loc_mean.shape[0])
+        with pytest.raises(ValueError, match="data_batch"):
+            m(**bad)
+        out, _ = m(**inp)                                         # a failed call leaves no dirty workspace behind
+        ref, _ = orc.forward(m.state_dict(), **inp)
+        assert max_abs(out, ref) <= 1e-5
+
+
+def test_edge_index_out_of_range_raises():
+    m = _tiny_model()
+    inp = _tiny_inputs()
+    ei = inp["edge_index"].clone()
+    ei[1, 3] = inp["node_loc"].shape[0]                          # one past the last node
+    with torch.no_grad(), pytest.raises(ValueError, match="edge_index"):
+        m(**dict(inp, edge_index=ei))
+    ei[1, 3] = -1
+    with torch.no_grad(), pytest.raises(ValueError, match="edge_index"):
+        m(**dict(inp, edge_index=ei))
+
+
+def test_csr_graph_rejects_wrong_dtypes_and_shapes():
+    from distegnn_b200.shards import CSRGraph
+    rowptr = torch.tensor([0, 2, 3], dtype=torch.int32)
+    col = torch.tensor([1, 0, 0], dtype=torch.int32)
+    CSRGraph(rowptr, col).validate()
+    with pytest.raises(ValueError, match="int32"):
+        CSRGraph(rowptr.long(), col)                              # e.g. the output of torch.cumsum
+    with pytest.raises(ValueError, match="int32"):
+        CSRGraph(rowptr, col.long())
+    with pytest.raises(ValueError, match="valid CSR"):
+        CSRGraph(torch.tensor([0, 2, 4], dtype=torch.int32), col).validate()      # rowptr[-1] != E
+    with pytest.raises(ValueError, match="valid CSR"):
+        CSRGraph(rowptr, torch.tensor([1, 0, 5], dtype=torch.int32)).validate()    # column id out of range
+
+
+def test_inputs_requiring_grad_warn_in_training_path():
+    m = _tiny_model().train()
+    inp = _tiny_inputs()
+    inp["node_loc"] = inp["node_loc"].clone().requires_grad_(True)
+    with pytest.warns(RuntimeWarning, match="treats inputs as constants"):
+        out, _ = m(**inp)
+    out.sum().backward()
+    assert inp["node_loc"].grad is None
