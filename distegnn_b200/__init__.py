@@ -5,5 +5,6 @@ Public surface mirrors the reference: ``from distegnn_b200 import FastEGNN`` is 
 """
 from .fast_egnn import E_GCL_vel, FastEGNN  # noqa: F401
 from .graph import radius_graph, split_large_graph_random  # noqa: F401  (on-device graph construction)
+from .loss import train_loss  # noqa: F401  (fused weighted-MSE + MMD loss of the training step)
 
-__all__ = ["FastEGNN", "E_GCL_vel", "radius_graph", "split_large_graph_random"]
+__all__ = ["FastEGNN", "E_GCL_vel", "radius_graph", "split_large_graph_random", "train_loss"]

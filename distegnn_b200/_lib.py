@@ -33,8 +33,11 @@ SIGNATURES = {
     "distegnn_build_csr": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "distegnn_gather_rows": [_vp, _vp, _i64, _i32, _vp, _vp],
     "distegnn_embed_fwd": [_i64, _i32, _i32, _i32, _i32, _i32] + [_vp] * 15,
-    "distegnn_edge_layer_fwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
-    "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 14,
+    "distegnn_edge_layer_fwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 11,
+    "distegnn_edge_layer_bwd": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 15,
+    "distegnn_radius_csr_workspace_bytes": [_i64, _i64, C.POINTER(_i64)],
+    "distegnn_radius_graph_csr": [_i64, _i32, _vp, _vp, C.c_float, _i32, _i32, _i64, _i64] + [_vp] * 6 + [_i64, _vp],
+    "distegnn_kmeans_lloyd": [_i64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_float, _i32, _vp],
     "distegnn_virtual_layer_bwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 16,
     "distegnn_virtual_bwd_prepare": [_i32, _i32, _i32, _vp, _vp, _vp],
     "distegnn_radius_count": [_i64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, _i32, _vp, _vp],
@@ -49,6 +52,9 @@ SIGNATURES = {
     "distegnn_comm_status": [_vp, C.POINTER(_i32)],
     "distegnn_comm_destroy": [_vp],
     "distegnn_allreduce_packed": [_vp, _vp, _i64, _vp],
+    "distegnn_loss_packed_floats": [_i32, _i32],
+    "distegnn_loss_partials": [_i64, _i32, _i32, _i32, _i32, _i32, C.c_float] + [_vp] * 10,
+    "distegnn_loss_finalize": [_i64, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _i32] + [_vp] * 10,
 }
 ABI_VERSION = 2
 

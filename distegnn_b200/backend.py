@@ -74,19 +74,22 @@ class CudaBackend:
                                           ptr(n_invalid), self._s(h)), "embed_fwd")
         self.launches += 1 if N else 0
 
-    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x) -> None:
+    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x, n_edges_dev=None) -> None:
+        """`n_edges_dev`: int32 [1] on the device with the true edge count when E is only a capacity (CSRGraph built on the
+        device without a host round trip)."""
         N, E, A, Cn, Na = dims
         check(self.lib.distegnn_edge_layer_fwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea),
                                                ptr(x4), ptr(P), ptr(Q), ptr(lp), ptr(agg_m), ptr(agg_x),
-                                               self._s(x4)), "edge_layer_fwd")
+                                               ptr(n_edges_dev), self._s(x4)), "edge_layer_fwd")
         self.launches += 1 if E else 0
 
-    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp) -> None:
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp,
+                       n_edges_dev=None) -> None:
         """Backward of edge_layer: accumulates into g_P, g_Q, g_x4 and the parameter-gradient block g_lp."""
         N, E, A, Cn, Na = dims
         check(self.lib.distegnn_edge_layer_bwd(N, E, A, Cn, Na, flags, ptr(row), ptr(col), ptr(ea), ptr(x4), ptr(P),
                                                ptr(Q), ptr(lp), ptr(g_agg_m), ptr(g_agg_x), ptr(g_P), ptr(g_Q),
-                                               ptr(g_x4), ptr(g_lp), self._s(x4)), "edge_layer_bwd")
+                                               ptr(g_x4), ptr(g_lp), ptr(n_edges_dev), self._s(x4)), "edge_layer_bwd")
         self.launches += 1 if E else 0
 
     def virtual_bwd_prepare(self, A, Cn, Na, lp) -> "torch.Tensor":

@@ -6,6 +6,8 @@
 #include <set>
 #include <utility>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace degnn {
@@ -105,6 +107,45 @@ void ensure_dynamic_smem(const void* kernel, int bytes) {
     if (done.count({dev, kernel})) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     done.insert({dev, kernel});
+}
+
+// Tensor map over a row-major fp32 matrix [n_rows][row_floats] for TMA row gathers: box = {box_floats, box_rows}.  A box
+// wider than the row (box_floats > row_floats) is legal — the out-of-bounds tail is zero-filled — and gives the rows a
+// padded pitch of box_floats in shared memory.  cuTensorMapEncodeTiled is a host-only driver call (no stream, no sync);
+// its entry point is resolved through the runtime, so the library has no link-time dependency on libcuda.
+int make_rows_tmap(void* out_map, const float* base, int64_t n_rows, int row_floats, int box_floats, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+                (void)cudaGetLastError();
+                set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+                return DISTEGNN_ECUDA;
+            }
+            fn = (EncodeFn)p;
+        }
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_floats, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, %lld rows x %d floats, box %d x %d)", (int)r,
+                  (const void*)base, (long long)n_rows, row_floats, box_floats, box_rows);
+        return DISTEGNN_ECUDA;
+    }
+    return DISTEGNN_OK;
 }
 
 }  // namespace degnn

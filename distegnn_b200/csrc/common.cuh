@@ -46,6 +46,8 @@ int sm_count();   // cached multiprocessor count of the current device
 // Opt `kernel` in to `bytes` of dynamic shared memory, once per (device, kernel).  Not a stream operation, so it is
 // done on the first (eager) call and never again — nothing but launches happens under CUDA-graph capture.
 void ensure_dynamic_smem(const void* kernel, int bytes);
+// 128-byte CUtensorMap over a row-major fp32 matrix for TMA row gathers (api.cu); out_map points to a CUtensorMap.
+int make_rows_tmap(void* out_map, const float* base, int64_t n_rows, int row_floats, int box_floats, int box_rows);
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float silu(float x) {

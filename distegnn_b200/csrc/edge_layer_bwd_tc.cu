@@ -26,6 +26,7 @@ namespace degnn {
 
 struct EdgeBwdTcArgs {
     int64_t N, E;
+    const int32_t* E_dev;   // optional device-side edge count (E = capacity)
     int A;
     unsigned flags;
     const int32_t* row;
@@ -184,11 +185,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) edge_layer_bwd_tc_kernel(const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) gW2[i][j] = gWc[i][j] = 0.f;
 
-    const int64_t num_tiles = (a.E + TILE_M - 1) / TILE_M;
+    const int64_t nE = a.E_dev ? min((int64_t)__ldg(a.E_dev), a.E) : a.E;
+    const int64_t num_tiles = (nE + TILE_M - 1) / TILE_M;
     for (int64_t tile = (int64_t)blockIdx.x * BT_GROUPS + grp; tile < num_tiles; tile += (int64_t)gridDim.x * BT_GROUPS) {
         // ---- the thread's edge: ids, attributes, geometry, upstream scalars ---------------------------------------
         const int64_t e = tile * TILE_M + t;
-        const bool valid = e < a.E;
+        const bool valid = e < nE;
         const int r = valid ? __ldg(a.row + e) : -1;
         const int c = valid ? __ldg(a.col + e) : 0;
         const int rr = max(r, 0);
@@ -398,7 +400,7 @@ extern "C" int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A, 
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q, const float* layer_params,
                                        const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q, float* g_x4,
-                                       float* g_layer_params, void* stream) {
+                                       float* g_layer_params, const int32_t* n_edges_dev, void* stream) {
     using namespace degnn;
     if (int rc = check_dims(A, C, Na)) return rc;
     if (n_edges == 0) return DISTEGNN_OK;
@@ -408,7 +410,7 @@ extern "C" int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A, 
     DEGNN_CHECK_ARG(A == 0 || edge_attr_sorted, "null edge_attr with edge_attr_nf > 0");
     Layout L = make_layout(A, C, Na);
     EdgeBwdTcArgs a;
-    a.N = n_nodes; a.E = n_edges; a.A = A; a.flags = flags;
+    a.N = n_nodes; a.E = n_edges; a.E_dev = n_edges_dev; a.A = A; a.flags = flags;
     a.row = row; a.col = col; a.ea = edge_attr_sorted; a.x4 = x4; a.P = P; a.Q = Q;
     a.w1r = layer_params + L.off[DISTEGNN_P_E_W1R];
     a.w1e = layer_params + L.off[DISTEGNN_P_E_W1E];

@@ -23,7 +23,9 @@
 // group takes the cold path (row maxima exchanged through shared memory, two more barriers).
 // The next tile's (row, col, edge_attr) are staged into shared memory with LDGSTS one stage ahead (double
 // buffered), its Q rows by TMA bulk copies issued 16 per warp from those staged indices.
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc16.cuh"
@@ -33,6 +35,7 @@ namespace degnn {
 
 struct EdgeCsArgs {
     int64_t N, E;
+    const int32_t* E_dev;   // optional: the edge count on the device (graphs built without a host round trip); E = capacity
     int A;
     unsigned flags;
     const int32_t* row;
@@ -52,8 +55,22 @@ struct EdgeCsArgs {
     float* agg_x;
 };
 
+// A/B build knobs (python -m distegnn_b200.build --variant ... --defs=-DCS_GATHER4=0):
+//   CS_GATHER4    1: the next tile's Q rows arrive FOUR per instruction through a tensor map over Q [N,64] whose box is 72
+//                    floats wide (the 8 out-of-bounds floats are zero-filled), i.e. 32 UTMALDG.GATHER4 per tile at a row
+//                    pitch of 72 floats; 0: one cp.async.bulk per row (128 UBLKCP per tile, 9 instructions each) at pitch 68
+//   CS_SEGSUM_V2  1: segment sum of m as one straight pass over the warp's 16 edges with a flush at run starts;
+//                    0: loop over runs with an inner loop per run (r01)
+#ifndef CS_GATHER4
+#define CS_GATHER4 1
+#endif
+#ifndef CS_SEGSUM_V2
+#define CS_SEGSUM_V2 1
+#endif
 constexpr int CS_THREADS = 1024, CS_GROUPS = 4, CS_GROUP = 256, CS_WARPS = 8;
-constexpr int CS_QROW = 68;                               // padded row pitch of the staging buffer (floats)
+// padded row pitch of the staging buffer (floats): 68 = conflict-free row-per-thread LDS.128 / STS.128; 72 (2-way
+// conflicts) keeps every 4-row gather box (4 x 288 B) 128-byte aligned, as TMA tensor copies require
+constexpr int CS_QROW = CS_GATHER4 ? 72 : 68;
 constexpr int CS_QBUF = TILE_M * CS_QROW;
 constexpr int CS_W = 64 * 64;                             // fp16 elements per weight matrix (8 KB)
 constexpr int CS_IDX = TILE_M * 4;                        // ints per index buffer: row 128 | col 128 | ea 128x2
@@ -98,7 +115,8 @@ __device__ __forceinline__ float max8(const f32x2 (&v)[4], float fm) {
 }
 
 template <int AT>
-__global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const EdgeCsArgs a) {
+__global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const EdgeCsArgs a,
+                                                                      const __grid_constant__ CUtensorMap tmQ) {
     using namespace umma;
     constexpr int AMAX = AT >= 0 ? (AT > 0 ? AT : 1) : DISTEGNN_MAX_EDGE_ATTR;
     constexpr bool kEaStaged = (AT == 1 || AT == 2);
@@ -171,7 +189,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     uint64_t* mbar = bars + grp * 2 + 1;
     const uint32_t bar_id = 1 + grp;
 
-    const int64_t num_tiles = (a.E + TILE_M - 1) / TILE_M;
+    const int64_t nE = a.E_dev ? min((int64_t)__ldg(a.E_dev), a.E) : a.E;     // valid edges (<= the host-side bound)
+    const int64_t num_tiles = (nE + TILE_M - 1) / TILE_M;
     const int64_t stride = (int64_t)gridDim.x * CS_GROUPS;
     int64_t tile = (int64_t)blockIdx.x * CS_GROUPS + grp;
 
@@ -195,7 +214,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     // start the copy of tile tl's (row, col, edge_attr) of edge r into index buffer `b` (threads of half 0)
     auto stage_idx = [&](int64_t tl, int b) {
         const int64_t e = tl * TILE_M + r;
-        if (tl < num_tiles && e < a.E) {
+        if (tl < num_tiles && e < nE) {
             int* dst = nidx + b * CS_IDX;
             cp_async4(dst + r, a.row + e);
             cp_async4(dst + TILE_M + r, a.col + e);
@@ -223,7 +242,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     if (tile < num_tiles) {
         const int64_t e = tile * TILE_M + r;
         int col_c = 0;
-        if (e < a.E) {
+        if (e < nE) {
             row_c = __ldg(a.row + e);
             col_c = __ldg(a.col + e);
 #pragma unroll
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 if (AT < 0 ? k < A : true) ea_c[k] = (k < A) ? __ldg(a.ea + e * A + k) : 0.f;
         }
         if (tg == 0) {
-            const int64_t nvalid = min((int64_t)TILE_M, a.E - tile * TILE_M);
+            const int64_t nvalid = min((int64_t)TILE_M, nE - tile * TILE_M);
             mbar_expect_tx(qbar, (uint32_t)nvalid * (H * 4));
         }
         if (hf == 0 && row_c >= 0) bulk_g2s(qb + r * CS_QROW, a.Q + (size_t)col_c * H, H * 4, qbar);
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         const int* nrow_s = nidx + nb * CS_IDX;
         const int* ncol_s = nrow_s + TILE_M;
         const float* nea_s = reinterpret_cast<const float*>(ncol_s + TILE_M);
-        const bool nvalid_r = ntile < num_tiles && ntile * TILE_M + r < a.E;     // edge r of the next tile exists
+        const bool nvalid_r = ntile < num_tiles && ntile * TILE_M + r < nE;     // edge r of the next tile exists
 
         // ---- stage 1: a1 = SiLU(P_i + Q_j + w_r·r + W_e·a), own 32 columns -> fp16 hi/lo -> TMEM ---------------
         mbar_wait(qbar, (uint32_t)(it & 1));
@@ -405,6 +424,32 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             // warp wk <-> edges 16wk .. 16wk+15 of the tile, lane <-> columns 2·lane, 2·lane+1: per edge one LDS.64
             // and one FADD2; the run structure is warp-uniform, one RED.v2 per run and lane
             const float* colp = qb + (16 * wk) * CS_QROW + 2 * lane;
+#if CS_SEGSUM_V2
+            // one straight pass over the warp's 16 edges; bit e of M = edge e starts a new run of equal destination rows
+            // (warp-uniform), where the running sum is flushed with one RED.v2 per lane
+            const uint32_t M = (rmask[wk >> 1] >> (16 * (wk & 1))) & 0xffffu;
+            const int* srw = srow + 16 * wk;
+            auto flush = [&](f32x2 acc, int e_last) {
+                const int rr = srw[e_last];
+                if (rr >= 0) {
+                    float v0, v1;
+                    upk2(acc, v0, v1);
+                    red_add_v2(a.agg_m + (size_t)rr * H + 2 * lane, v0, v1);
+                }
+            };
+            f32x2 s0 = *reinterpret_cast<const f32x2*>(colp);
+#pragma unroll
+            for (int e = 1; e < 16; ++e) {
+                const f32x2 v = *reinterpret_cast<const f32x2*>(colp + e * CS_QROW);
+                if ((M >> e) & 1u) {
+                    flush(s0, e - 1);
+                    s0 = v;
+                } else {
+                    s0 = add2(s0, v);
+                }
+            }
+            flush(s0, 15);
+#else
             uint32_t M = ((rmask[wk >> 1] >> (16 * (wk & 1))) & 0xffffu) | 1u;
             while (M) {
                 const int e0 = __ffs((int)M) - 1;
@@ -426,19 +471,36 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                     red_add_v2(a.agg_m + (size_t)rr * H + 2 * lane, v0, v1);
                 }
             }
+#endif
         }
         fence_proxy_async_smem();              // generic accesses to qb ordered before the TMA refill below
         named_bar(bar_id, CS_GROUP);           // whole group done with the staging buffer
 
-        // ---- Q rows of the next tile: 16 bulk copies per warp, addresses from the staged indices -------------------
+        // ---- Q rows of the next tile, addresses from the staged indices ----------------------------------------------------
         if (ntile < num_tiles) {
+#if CS_GATHER4
+            // 4 rows per instruction: every warp's elected lane issues 4 gathers for the warp's 16 edges.  Always the whole
+            // tile (32 x 4 x 288 bytes): indices past the last edge are stale shared memory, and a row coordinate outside
+            // [0,N) is zero-filled by the TMA unit rather than faulting.
+            if (tg == 0) mbar_expect_tx(qbar, (uint32_t)(TILE_M * CS_QROW * 4));
+            __syncwarp();
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int4 c4 = *reinterpret_cast<const int4*>(ncol_s + 16 * wk + 4 * i);
+                    tma_gather4(qb + (16 * wk + 4 * i) * CS_QROW, &tmQ, 0, c4.x, c4.y, c4.z, c4.w, qbar);
+                }
+            }
+            __syncwarp();
+#else
             if (tg == 0) {
-                const int64_t nvalid = min((int64_t)TILE_M, a.E - ntile * TILE_M);
+                const int64_t nvalid = min((int64_t)TILE_M, nE - ntile * TILE_M);
                 mbar_expect_tx(qbar, (uint32_t)nvalid * (H * 4));
             }
             const int rr = 16 * wk + (lane & 15);
-            if (lane < 16 && ntile * TILE_M + rr < a.E)
+            if (lane < 16 && ntile * TILE_M + rr < nE)
                 bulk_g2s(qb + rr * CS_QROW, a.Q + (size_t)ncol_s[rr] * H, H * 4, qbar);
+#endif
         }
         // coordinates of the next tile's edge (consumed after stage 3)
         int row_n = -1;
@@ -534,7 +596,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
 extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                                        const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                        const float* x4, const float* P, const float* Q,
-                                       const float* layer_params, float* agg_m, float* agg_x, void* stream) {
+                                       const float* layer_params, float* agg_m, float* agg_x,
+                                       const int32_t* n_edges_dev, void* stream) {
     using namespace degnn;
     if (int rc = check_dims(A, C, Na)) return rc;
     if (n_edges == 0) return DISTEGNN_OK;
@@ -544,7 +607,7 @@ extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, 
     DEGNN_CHECK_ARG((flags & DISTEGNN_FLAG_LAST) || agg_m, "null agg_m");
     Layout L = make_layout(A, C, Na);
     EdgeCsArgs a;
-    a.N = n_nodes; a.E = n_edges; a.A = A; a.flags = flags;
+    a.N = n_nodes; a.E = n_edges; a.E_dev = n_edges_dev; a.A = A; a.flags = flags;
     a.row = row; a.col = col; a.ea = edge_attr_sorted; a.x4 = x4; a.P = P; a.Q = Q;
     a.w1r = layer_params + L.off[DISTEGNN_P_E_W1R];
     a.w1e = layer_params + L.off[DISTEGNN_P_E_W1E];
@@ -557,9 +620,15 @@ extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, 
     const int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
     int64_t grid = (tiles + CS_GROUPS - 1) / CS_GROUPS;
     if (grid > sm_count()) grid = sm_count();
+    CUtensorMap tmQ;
+    memset(&tmQ, 0, sizeof(tmQ));
+#if CS_GATHER4
+    // Q [N,64] as a 2-D tensor; box 72 x 1: four gathered rows land as 4 x 72 floats (the tail zero-filled)
+    if (int rc = make_rows_tmap(&tmQ, Q, n_nodes, H, CS_QROW, 1)) return rc;
+#endif
     auto launch = [&](auto kern) {
         ensure_dynamic_smem((const void*)kern, (int)CS_SMEM_BYTES);
-        kern<<<(unsigned)grid, CS_THREADS, CS_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+        kern<<<(unsigned)grid, CS_THREADS, CS_SMEM_BYTES, (cudaStream_t)stream>>>(a, tmQ);
     };
     switch (A) {
         case 0: launch(edge_layer_cs_kernel<0>); break;

@@ -2,6 +2,8 @@
 // with the 3xTF32 split, A through TMEM (variant 0/1) or shared memory (variant 2/3), B through the no-swizzle
 // K-major shared-memory descriptor.  Exposed through the C ABI so tests/test_gpu_parity.py can pin the
 // descriptor encodings on real hardware.
+#include <cuda.h>
+
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -240,6 +242,56 @@ extern "C" int distegnn_selftest_umma(const float* A, const float* W,
     const int smem = 2 * 16384 + 2 * 32768;
     cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, variant);
+    DEGNN_CHECK_LAUNCH();
+    return DISTEGNN_OK;
+}
+
+// ---- TMA gather4 building-block self-test ---------------------------------------------------------------------------
+// out[g][4][box_floats] = the 4 rows idx[4g..4g+3] of src [n_rows][64] fetched by ONE cp.async.bulk.tensor ...tile::gather4
+// each, through a tensor map whose box is WIDER than the row (box_floats = 72 > 64): the out-of-bounds tail must come back
+// as zeros and the rows must land at a pitch of box_floats — the layout the edge kernel's staging buffer relies on.
+namespace degnn {
+__global__ void __launch_bounds__(128) gather4_selftest_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* idx,
+                                                               int n_groups, int box_floats, float* out) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* buf = reinterpret_cast<float*>(smem_raw);
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_groups * 4 * box_floats; i += blockDim.x) buf[i] = -7.0f;      // sentinel
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&bar, (uint32_t)(n_groups * 4 * box_floats * 4));
+        __syncwarp();
+        if (elect_one()) {
+            for (int g = 0; g < n_groups; ++g) {
+                const int4 r = *reinterpret_cast<const int4*>(idx + 4 * g);
+                tma_gather4(buf + g * 4 * box_floats, &tm, 0, r.x, r.y, r.z, r.w, &bar);
+            }
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    for (int i = tid; i < n_groups * 4 * box_floats; i += blockDim.x) out[i] = buf[i];
+}
+}  // namespace degnn
+
+extern "C" int distegnn_selftest_gather4(const float* src, int64_t n_rows, const int32_t* idx, int n_groups,
+                                         int box_floats, int box_rows, float* out, void* stream) {
+    using namespace degnn;
+    DEGNN_CHECK_ARG(src && idx && out && n_groups >= 1 && n_groups <= 32, "bad argument");
+    DEGNN_CHECK_ARG(box_floats >= 64 && box_floats <= 256 && box_floats % 4 == 0, "bad box width");
+    CUtensorMap tm;
+    if (int rc = make_rows_tmap(&tm, src, n_rows, 64, box_floats, box_rows)) return rc;
+    const int smem = n_groups * 4 * box_floats * 4;
+    ensure_dynamic_smem((const void*)gather4_selftest_kernel, smem);
+    gather4_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tm, idx, n_groups, box_floats, out);
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;
 }

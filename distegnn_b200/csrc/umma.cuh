@@ -211,6 +211,25 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// One lane of the (converged) warp, chosen by the hardware.  Code under `if (elect_one())` is known to ptxas to run in a
+// single lane, so per-thread values feeding UBLKCP / UTCHMMA operands move to uniform registers with plain R2URs — no
+// ELECT / R2UR / PLOP3 / BRA.ANY loop over the active lanes (9 instructions per bulk copy otherwise).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e != 0;
+}
+
+// ---- TMA row gather: FOUR rows of a 2-D tensor (tensor map) per instruction into 4 consecutive box rows -------------
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, int c0, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+        "%5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- bulk async copy shared -> global (TMA engine), tracked by the issuing thread's bulk async-group --------------
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),

@@ -347,10 +347,10 @@ class FastEGNN(nn.Module):
                                               edge_index, data_batch, edge_attr, node_attr)
             with torch.no_grad():
                 pk = self._packed_params(dev)
-                rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
+                rowptr, row, col, ea, nE = self._csr_inputs(be, edge_index, edge_attr, N, f32)
                 args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
                             loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
-                            data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
+                            data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea, nE=nE)
                 dims = (N, E, B, K)
                 comm = self._get_comm(be, dev, B, K)
                 graph_ok = self.world_size == 1 or comm is not None      # NCCL calls are not captured
@@ -387,10 +387,10 @@ class FastEGNN(nn.Module):
         A = self.edge_attr_nf
         if isinstance(edge_index, CSRGraph):
             return (edge_index.rowptr.contiguous(), edge_index.rows().contiguous(), edge_index.col.contiguous(),
-                    f32(edge_attr) if A > 0 else None)
+                    f32(edge_attr) if A > 0 else None, edge_index.n_edges_dev)
         rowptr, row, col, perm = self._graphs.get(be, edge_index, N, self.validate_inputs)
         ea = self._graphs.sorted_edge_attr(be, edge_index, edge_attr, perm) if A > 0 else None
-        return rowptr, row, col, ea
+        return rowptr, row, col, ea, None
 
     # ---- training path -----------------------------------------------------------------
     def _forward_autograd(self, be, dev, dims, f32, node_feat, node_loc, node_vel, loc_mean, edge_index, data_batch,
@@ -407,10 +407,10 @@ class FastEGNN(nn.Module):
         emb_b = self.embedding_in.bias.to(device=dev, dtype=torch.float32)
         hv0 = self.virtual_node_feat[0].t().contiguous().to(device=dev, dtype=torch.float32)          # [C,64]
         with torch.no_grad():
-            rowptr, row, col, ea = self._csr_inputs(be, edge_index, edge_attr, N, f32)
+            rowptr, row, col, ea, nE = self._csr_inputs(be, edge_index, edge_attr, N, f32)
             args = dict(node_feat=f32(node_feat), node_loc=f32(node_loc), node_vel=f32(node_vel),
                         loc_mean=f32(loc_mean), attr=f32(node_attr) if Na > 0 else None,
-                        data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea)
+                        data_batch=data_batch.contiguous(), rowptr=rowptr, row=row, col=col, ea=ea, nE=nE)
         return _FastEGNNFunction.apply(self, be, dims, args, emb_wt, emb_b, hv0, *lps)
 
     def _run_saving(self, be, dims, a: Dict[str, Tensor], emb_wt, emb_b, hv0, layers: List[Tensor]):
@@ -446,7 +446,7 @@ class FastEGNN(nn.Module):
             agg_x, trans_v, vs = zeros(N, 4), new(N, 4), zeros(B, K)
             agg_m = None if last else zeros(N, H)
             agg_v = None if last else new(N, H)
-            be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp, agg_m, agg_x)
+            be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp, agg_m, agg_x, a["nE"])
             be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp, agg_v, trans_v, vs)
             x4n = new(N, 4)
             hn, Pn, Qn, Hnn = (None,) * 4 if last else (new(N, H), new(N, H), new(N, H), new(N, H))
@@ -529,7 +529,7 @@ class FastEGNN(nn.Module):
             lp, lp_next = layers[i], (None if last else layers[i + 1])
             t0 = self._mark("edge")
             be.edge_layer((N, E, A, Cn, Na), flags, a["row"], a["col"], a["ea"], x4, P, Q, lp,
-                          None if last else agg_m, agg_x)
+                          None if last else agg_m, agg_x, a["nE"])
             t1 = self._mark("edge_end")
             be.virtual_layer((N, B, A, Cn, Na), flags, batch32, x4, Hn, Xv, G, lp,
                              None if last else agg_v, trans_v, vsum)
@@ -675,7 +675,7 @@ class _FastEGNNFunction(torch.autograd.Function):
             # ---- 4. per-edge stage (CUDA) --------------------------------------------------------------------------------
             g_P_i, g_Q_i, g_x4e = zeros(N, H), zeros(N, H), zeros(N, 4)
             be.edge_layer_bwd((N, E, A, Cn, Na), S["flags"], a["row"], a["col"], a["ea"], S["x4"], S["P"], S["Q"], lp,
-                              g_agg_m, g_agg_x, g_P_i, g_Q_i, g_x4e, g_lps[i])
+                              g_agg_m, g_agg_x, g_P_i, g_Q_i, g_x4e, g_lps[i], a["nE"])
             g_x = g_x_i + g_xv[:, :3] + g_x4e[:, :3]
             g_h, g_P, g_Q, g_Hn = g_h_i, g_P_i, g_Q_i, g_Hn_i
             g_Xv, g_Hv, g_G = g_Xv_acc, g_Hv_i, g_G_i

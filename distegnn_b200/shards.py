@@ -32,6 +32,10 @@ class CSRGraph:
     rowptr: Tensor
     col: Tensor
     row: Optional[Tensor] = None
+    # graphs built on the device without a host round trip (partition.radius_graph_csr(capacity=...)): `col` / `row` /
+    # edge_attr are CAPACITY-sized, the true edge count lives on the device and the kernels read it there
+    n_edges_dev: Optional[Tensor] = None
+    info: Optional[Tensor] = None
 
     def __post_init__(self):
         self._checked = None
@@ -53,7 +57,7 @@ class CSRGraph:
         once per CSRGraph object."""
         if device is not None and self.rowptr.device != device:
             raise ValueError(f"CSRGraph lives on {self.rowptr.device}, the node tensors on {device}")
-        if self._checked:
+        if self._checked or self.n_edges_dev is not None:     # device-built: valid by construction, count not on the host
             return
         N, E = self.num_nodes, self.num_edges
         ok = int(self.rowptr[0]) == 0 and int(self.rowptr[-1]) == E
@@ -64,6 +68,10 @@ class CSRGraph:
         if not ok:
             raise ValueError("CSRGraph is not a valid CSR: rowptr must be non-decreasing from 0 to E and col in [0, N)")
         self._checked = True
+
+    def overflowed(self) -> bool:
+        """Device-built graph only: did the edge count exceed the capacity (then edges are missing)?  Synchronises."""
+        return self.info is not None and int(self.info[1].item()) != 0
 
     @property
     def num_nodes(self) -> int:

@@ -167,12 +167,16 @@ DISTEGNN_API int distegnn_embed_fwd(int64_t n_nodes, int n_graphs, int F, int A,
  *   m  = SiLU(W2·SiLU(P_i + Q_j + w_r·r + W_e·a_ij) + b2),  φ = w3·SiLU(Wc·m + bc)
  *   agg_m[i] += m   (skipped with FLAG_LAST),   agg_x[i].xyz += Δx·φ
  * Sums, not means: the division by max(deg,1) happens in distegnn_node_layer_fwd.  The caller zeroes
- * agg_m [N,64] and agg_x [N,4] before the call.
+ * agg_m [N,64] and agg_x [N,4] before the call.  For graphs built on the device without a host round trip
+ * (distegnn_radius_graph_csr with a capacity) n_edges is the CAPACITY of row/col/edge_attr and n_edges_dev points to the
+ * true count, which the kernel reads itself.
  */
 DISTEGNN_API int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, int C, int Na, unsigned flags,
                             const int32_t *row, const int32_t *col, const float *edge_attr_sorted,
                             const float *x4, const float *P, const float *Q,
-                            const float *layer_params, float *agg_m, float *agg_x, void *stream);
+                            const float *layer_params, float *agg_m, float *agg_x,
+                            const int32_t *n_edges_dev /*NULL, or the edge count on the device (<= n_edges)*/,
+                            void *stream);
 
 /* Backward of distegnn_edge_layer_fwd (in the reference: autograd through models/FastEGNN.py:144-150,
  * 169-177, 206, 237-246, 322-337).  Nothing of size [E,.] is kept from the forward pass: every 128-edge tile is
@@ -184,7 +188,7 @@ DISTEGNN_API int distegnn_edge_layer_bwd(int64_t n_nodes, int64_t n_edges, int A
                                          const int32_t* row, const int32_t* col, const float* edge_attr_sorted,
                                          const float* x4, const float* P, const float* Q, const float* layer_params,
                                          const float* g_agg_m, const float* g_agg_x, float* g_P, float* g_Q,
-                                         float* g_x4, float* g_layer_params, void* stream);
+                                         float* g_x4, float* g_layer_params, const int32_t* n_edges_dev, void* stream);
 
 /* Backward of distegnn_virtual_layer_fwd (in the reference: autograd through models/FastEGNN.py:154-163,
  * 180, 191-193, 207, 220-223, 252-253).  Rows are recomputed tile by tile; the six row-wise tile GEMMs run on tcgen05.
@@ -220,6 +224,28 @@ DISTEGNN_API int distegnn_radius_fill(int64_t n_nodes, const float* x4, const in
                                       const int64_t* cell_start, const float* origin_host, float cell_size,
                                       const int32_t* dims_host, float radius, int loop, const int64_t* rowptr,
                                       int32_t* row, int32_t* col, float* dist, void* stream);
+
+/* On-device radius graph, CSR out, in ONE call and without a host round trip (csrc/radius_csr.cu): the
+ * reference-boundary tensors in (pos [N,3] fp32, data_batch int64 [N] sorted, may be NULL for one graph), int32 CSR by
+ * destination out (rowptr [N+1], row / col [capacity]) plus edge_attr [capacity, edge_attr_nf] = the edge length in every
+ * column (datasets/distribute_graphs.py:43-44).  Pairs with |x_i - x_j| < radius (strict, as torch_cluster), j != i unless
+ * `loop`, same graph only.  Bounding box, grid sizing (cell >= radius, grown until graphs x cells <= table_cells), cell
+ * keys, sort, counts and prefix sums all happen on the device; info [4] (device): [0] edges found, [1] 1 if that exceeds
+ * `capacity` (then only rowptr is complete), [2] cells used.  capacity = 0 runs the count only (row/col may be NULL). */
+DISTEGNN_API int distegnn_radius_csr_workspace_bytes(int64_t n_nodes, int64_t table_cells, int64_t *bytes_host);
+DISTEGNN_API int distegnn_radius_graph_csr(int64_t n_nodes, int n_graphs, const float *pos, const int64_t *data_batch,
+                                           float radius, int loop, int edge_attr_nf, int64_t capacity,
+                                           int64_t table_cells, int32_t *rowptr, int32_t *row, int32_t *col,
+                                           float *edge_attr, int32_t *info, void *workspace, int64_t workspace_bytes,
+                                           void *stream);
+
+/* Lloyd iterations of the k-means node partitioner (datasets/distribute_graphs.py:118-143, 188-198: sklearn KMeans on the
+ * host) with sklearn's stopping rules evaluated on the device: `iters` iterations are enqueued; once no label changes, or
+ * the squared centre shift is <= tol (then after one more assignment pass), the remaining ones are no-ops.  centers [K,3]
+ * in/out (seeded by the caller, k-means++), labels int32 [N] in/out (−1 initially), sums float64 [K,4] zeroed once by the
+ * caller, state int32 [4] zeroed once: [0] 0 running / 1 final pass pending / 2 converged, [1] iterations done. */
+DISTEGNN_API int distegnn_kmeans_lloyd(int64_t n_nodes, int n_clusters, const float *pos, float *centers,
+                                       int32_t *labels, double *sums, int32_t *state, float tol, int iters, void *stream);
 
 /* ---- real↔virtual stage --------------------------------------------------------------------------
  * Virtual geometry + edge_mode_virtual + the virtual parts of coord_model_vel, coord_model_virtual,
@@ -300,6 +326,29 @@ DISTEGNN_API int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na,
                                 float *Xv, float *Hv, const float *layer_params,
                                 const float *next_layer_params, float *G, const float *init_loc_mean,
                                 const float *init_hv0, void *comm, void *stream);
+
+/* ---- loss side of the training step -------------------------------------------------------------------
+ * Replaces utils/train.py:98-147: node-count weighted MSE (:98-110), the MMD regulariser between the virtual
+ * coordinates and S = samples·C sampled target positions per graph (:119-147, kernel k(x,y) = exp(−‖x−y‖₂/(2σ²)), :11-14)
+ * and the per-step scalar collectives (:104, :109 and the loc_mean all_gather check :52-61), folded into ONE packed SUM
+ * all-reduce issued by the caller between the two calls (distegnn_allreduce_packed or any SUM all-reduce).
+ *   packed [2 + world·3B]  (zeroed by the caller)  [0] n_r, [1] n_r·MSE_r, [2 + r·3B ...] rank r's loc_mean
+ *   acc    [3]             (zeroed by the caller)  Σ_b l_vv, Σ_b l_rv, n_r·MSE_r (local copies for the finalize)
+ *   graph_ptr [B+1] int64: first node of every graph (data_batch is sorted); samples [B,S] int32: node indices LOCAL to
+ *   the graph drawn by the caller (the reference uses torch.randperm(num_node)[:S] per graph; −1 pads graphs with fewer
+ *   than S nodes — the reference still divides by S)
+ * distegnn_loss_finalize (after the all-reduce): out[0] = loss to back-propagate = world·n_r/Σn·(MSE_r + weight·MMD_r) /
+ * accumulation_steps, out[1] = logged loss Σ_r n_r/Σn·MSE_r, out[2] = MMD_r, out[3] = max |loc_mean_r − loc_mean_0|, and
+ * the gradients of out[0]: g_pred [N,3], g_Xv [B,3,C] (cdist's convention: zero gradient at coincident points). */
+DISTEGNN_API int distegnn_loss_packed_floats(int n_graphs, int world);
+DISTEGNN_API int distegnn_loss_partials(int64_t n_nodes, int n_graphs, int C, int S, int world, int rank, float sigma,
+                                        const float *pred, const float *target, const float *Xv, const float *loc_mean,
+                                        const int64_t *graph_ptr, const int32_t *samples, float *acc, float *packed,
+                                        float *gV_raw, void *stream);
+DISTEGNN_API int distegnn_loss_finalize(int64_t n_nodes, int n_graphs, int C, int S, int world, int rank, float sigma,
+                                        float weight, int accumulation_steps, const float *pred, const float *target,
+                                        const float *loc_mean, const float *acc, const float *packed, const float *gV_raw,
+                                        float *g_pred, float *g_Xv, float *out, void *stream);
 
 #ifdef __cplusplus
 }

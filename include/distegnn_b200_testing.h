@@ -99,6 +99,12 @@ DISTEGNN_API int distegnn_node_layer_fwd_simt(int64_t n_nodes, int n_graphs, int
                                               float *P, float *Q, float *Hn, float *node_loc_out, float *vsum,
                                               void *stream);
 
+/* TMA gather4 building-block self-test: out [n_groups][4][box_floats] = rows idx[4g..4g+3] of src [n_rows][64], one
+ * cp.async.bulk.tensor ...tile::gather4 per group through a tensor map with box {box_floats, box_rows}; box_floats > 64
+ * exercises the zero-filled out-of-bounds tail that gives the rows a padded shared-memory pitch. */
+DISTEGNN_API int distegnn_selftest_gather4(const float *src, int64_t n_rows, const int32_t *idx, int n_groups,
+                                           int box_floats, int box_rows, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,7 @@ class ShadowBackend:
         vsum[:, 0:3].index_add_(0, data_batch, node_loc)
         vsum[:, 3].index_add_(0, data_batch, torch.ones(N, dtype=vsum.dtype, device=vsum.device))
 
-    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x):
+    def edge_layer(self, dims, flags, row, col, ea, x4, P, Q, lp, agg_m, agg_x, n_edges_dev=None):
         N, E, A, C, Na = dims
         if E == 0:
             return
@@ -170,7 +170,7 @@ class ShadowBackend:
 
     # ---- backward stand-ins (torch.autograd over tests/shadow_autograd.py): same accumulate / write contracts as
     # distegnn_edge_layer_bwd / distegnn_virtual_layer_bwd, so that FastEGNN's training path can run on CPU ---------
-    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp):
+    def edge_layer_bwd(self, dims, flags, row, col, ea, x4, P, Q, lp, g_agg_m, g_agg_x, g_P, g_Q, g_x4, g_lp, n_edges_dev=None):
         from tests import shadow_autograd as sa
         N, E, A, C, Na = dims
         if E == 0:

@@ -1132,3 +1132,151 @@ def test_multi_gpu_parity_under_torchrun(split_mode, extra):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     print(p.stdout[-3000:], p.stderr[-1500:])
     assert p.returncode == 0 and "DIST_PARITY PASS" in p.stdout
+
+
+@pytest.mark.gpu
+def test_tma_gather4_building_block():
+    """cp.async.bulk.tensor.2d ...tile::gather4 through a tensor map whose box (72 floats) is wider than the row (64):
+    four rows per instruction land at a pitch of 72 floats with a zero-filled tail — the padded staging layout of the edge
+    kernel — and out-of-range row coordinates come back as zeros instead of faulting."""
+    from tests.twin_backend import check, load_testing
+    lib = load_testing()
+    g = torch.Generator().manual_seed(0)
+    n_rows, groups = 1000, 5
+    src = torch.randn(n_rows, 64, generator=g).to(dev())
+    idx = torch.randint(0, n_rows, (4 * groups,), generator=g, dtype=torch.int32)
+    idx[5], idx[6] = n_rows + 3, -2                                  # out of bounds -> zeros
+    idx_d = idx.to(dev())
+    out = torch.empty(groups, 4, 72, device=dev())
+    check(lib.distegnn_selftest_gather4(src.data_ptr(), n_rows, idx_d.data_ptr(), groups, 72, 1, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "selftest_gather4")
+    torch.cuda.synchronize()
+    want = torch.zeros(groups * 4, 72, device=dev())
+    ok = (idx_d >= 0) & (idx_d < n_rows)
+    want[ok, :64] = src[idx_d[ok].long()]
+    assert torch.equal(out.reshape(groups * 4, 72), want)
+
+
+# ---- f-2: graph construction and partitioning on the device, CSR out ---------------------------------------------------
+def _csr_edge_set(g, ea=None):
+    E = g.num_edges if g.n_edges_dev is None else int(g.n_edges_dev.item())
+    row, col = g.rows()[:E].cpu().numpy().astype(np.int64), g.col[:E].cpu().numpy().astype(np.int64)
+    return set(zip(row.tolist(), col.tolist())), E
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,r,B,loop", [(5000, 0.075, 1, False), (3000, 0.1, 3, False), (400, 0.3, 2, True), (1, 0.5, 1, False)])
+def test_radius_graph_csr_matches_kdtree(n, r, B, loop):
+    """One C-ABI call, everything decided on the device: same edge set as scipy's cKDTree (pairs within one fp32 ulp of r
+    excepted), rows ascending (a valid CSR), edge_attr = the edge length in every column; capacity mode = same graph
+    without any host synchronisation."""
+    from scipy.spatial import cKDTree
+    from distegnn_b200.partition import radius_graph_csr
+    rng = np.random.default_rng(7)
+    pos = rng.uniform(0, 1.0, size=(n, 3)).astype(np.float32)
+    batch = np.sort(rng.integers(0, B, size=n)).astype(np.int64)
+    batch[0], batch[-1] = 0, B - 1
+    want, near = set(), set()
+    for b in range(B):
+        idx = np.nonzero(batch == b)[0]
+        if len(idx) == 0:
+            continue
+        t = cKDTree(pos[idx].astype(np.float64))
+        for i, j in t.query_pairs(r * (1 + 1e-6), output_type="ndarray"):
+            d = float(np.linalg.norm(pos[idx[i]].astype(np.float64) - pos[idx[j]].astype(np.float64)))
+            pair = {(int(idx[i]), int(idx[j])), (int(idx[j]), int(idx[i]))}
+            (near if abs(d - r) <= 2e-7 * max(r, 1.0) else want).update(pair) if d < r * (1 + 1e-6) else None
+        if loop:
+            want.update((int(i), int(i)) for i in idx)
+    pd, bd = torch.from_numpy(pos).to(dev()), (torch.from_numpy(batch).to(dev()) if B > 1 else None)
+    g, ea = radius_graph_csr(pd, r, bd, loop=loop)
+    got, E = _csr_edge_set(g)
+    assert len(got) == E, "duplicate edges"
+    assert want - near <= got <= want | near
+    g.validate(dev())                                          # monotone rowptr ending at E, columns in range
+    if E:
+        rows, cols = g.rows().long(), g.col.long()
+        d = (pd[rows] - pd[cols]).norm(dim=1)
+        assert float((ea[:, 0] - d).abs().max()) <= 1e-6 and torch.equal(ea[:, 0], ea[:, 1])
+    gc, eac = radius_graph_csr(pd, r, bd, loop=loop, capacity=E + 100, n_graphs=B)
+    assert gc.n_edges_dev is not None and not gc.overflowed() and int(gc.n_edges_dev.item()) == E
+    assert torch.equal(gc.rowptr, g.rowptr) and torch.equal(gc.col[:E], g.col) and torch.equal(eac[:E], ea)
+    if E > 10:
+        small, _ = radius_graph_csr(pd, r, bd, loop=loop, capacity=E // 2, n_graphs=B)
+        assert small.overflowed()
+
+
+@pytest.mark.gpu
+def test_device_built_graph_feeds_the_model_without_host_sync():
+    """Rollout shape: positions change every step, the graph is rebuilt on the device with a capacity (no host read of the
+    edge count), the model reads the count on the device: same outputs as the host-built int64 edge_index path."""
+    from distegnn_b200.partition import radius_graph_csr
+    w = synth.WORKLOADS["fluid113k"]
+    inp = to_dev(synth.make_partitions(w, n_nodes=20_000, seed=3)[0])
+    sd = orc.init_state_dict(3, 2, 2, 64, 5, 4, seed=1, coord_gain=0.05)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=2, edge_attr_nf=2, virtual_channels=5, n_layers=4), sd)
+    node = {k: v for k, v in inp.items() if k not in ("edge_index", "edge_attr")}
+    with torch.no_grad():
+        ref, refX = m(**inp)
+        cap = int(inp["edge_index"].shape[1] * 1.3)
+        m(**node, **dict(zip(("edge_index", "edge_attr"), radius_graph_csr(inp["node_loc"], w.radius, capacity=cap))))   # warm-up
+        torch.cuda.synchronize()
+        pos = inp["node_loc"].clone()
+        outs = []
+        # the loop below must not synchronise: torch would raise on .item()/.cpu() under this guard
+        with torch.cuda.StreamContext(torch.cuda.current_stream()):
+            torch.cuda.set_sync_debug_mode("error")
+            try:
+                for step in range(3):
+                    g, ea = radius_graph_csr(pos, w.radius, capacity=cap)
+                    out, X = m(**dict(node, node_loc=pos), edge_index=g, edge_attr=ea)
+                    outs.append(out)
+                    pos = out                                  # next step starts from the predicted positions
+            finally:
+                torch.cuda.set_sync_debug_mode("default")
+        torch.cuda.synchronize()
+    assert max_abs(outs[0], ref) <= 2e-6 and not g.overflowed()
+    # step 2 against the reference path on the same positions
+    with torch.no_grad():
+        from distegnn_b200 import radius_graph
+        ei, ea2 = radius_graph(outs[0], w.radius)
+        want, _ = m(**dict(node, node_loc=outs[0]), edge_index=ei, edge_attr=ea2)
+    assert max_abs(outs[1], want) <= 5e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,P", [(30_000, 8), (113_140, 8), (20_000, 2)])
+def test_kmeans_on_device_matches_sklearn(n, P):
+    """Lloyd iterations on the device from sklearn's own k-means++ seeding: label agreement with
+    KMeans(n_clusters=P, random_state=0, n_init='auto').fit_predict (distribute_graphs.py:188-198)."""
+    from sklearn.cluster import KMeans
+    from distegnn_b200.partition import kmeans_labels
+    w = synth.WORKLOADS["fluid113k"]
+    pos = synth.make_points(w, seed=4, n_nodes=n)["pos"]
+    want = KMeans(n_clusters=P, random_state=0, n_init="auto").fit_predict(pos.astype(np.float32))
+    got = kmeans_labels(torch.from_numpy(pos).to(dev()), P).cpu().numpy()
+    agree = float((got == want).mean())
+    print(f"k-means n={n} P={P}: label agreement with sklearn {agree:.6f}, cluster sizes {np.bincount(got, minlength=P).tolist()}")
+    assert agree >= 0.999
+
+
+@pytest.mark.gpu
+def test_split_large_graph_on_device_kmeans_and_random():
+    """The device partitioner (k-means / random chunks + per-chunk CSR radius graphs) gives the same partitions as the host
+    restatement of distribute_graphs.py, and the model accepts them as they are."""
+    from distegnn_b200.partition import split_large_graph
+    w = synth.WORKLOADS["fluid113k"]
+    n, P = 24_000, 4
+    pts = synth.make_points(w, seed=6, n_nodes=n)
+    d = dev()
+    pos, vel = torch.from_numpy(pts["pos"]).to(d), torch.from_numpy(pts["vel"]).to(d)
+    feat, attr = torch.from_numpy(pts["feat"]).to(d), torch.from_numpy(pts["attr"]).to(d)
+    for mode in ("kmeans", "random"):
+        host = synth.make_partitions(w, world_size=P, split_mode=mode, seed=6, n_nodes=n)
+        mine = split_large_graph(pos, feat, pos + 0.01 * vel, vel, attr, w.radius, P, split_mode=mode,
+                                 generator=torch.Generator().manual_seed(6))
+        for r in range(P):
+            assert torch.equal(mine[r]["pos"].cpu(), host[r]["node_loc"]), (mode, r)
+            he = set(zip(host[r]["edge_index"][0].tolist(), host[r]["edge_index"][1].tolist()))
+            ge, E = _csr_edge_set(mine[r]["edge_index"])
+            assert len(ge ^ he) <= max(2, int(2e-5 * len(he))), (mode, r, len(ge ^ he))     # pairs within an ulp of r

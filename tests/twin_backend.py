@@ -28,6 +28,7 @@ TWIN_SIGNATURES = {
     "distegnn_edge_layer_fwd_simt": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_edge_layer_fwd_tf32": [_i64, _i64, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_selftest_umma": [_vp, _vp, _vp, _i32, _vp],
+    "distegnn_selftest_gather4": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp],
     "distegnn_virtual_layer_fwd_cs": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_virtual_layer_fwd_tf32": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_virtual_layer_fwd_simt": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
