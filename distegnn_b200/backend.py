@@ -151,6 +151,25 @@ class CudaBackend:
                                                ptr(loc_out), ptr(vsum), self._s(x4)), "node_layer_fwd")
         self.launches += 1 if N else 0
 
+    def node_layer_bwd(self, dims, flags, rowptr, batch32, h, vel, attr, agg_m, agg_v, lp, lp_next, g_x_out, g_vsum,
+                       g_h_out, g_P, g_Q, g_Hn, g_h, g_x, g_agg_x, g_trans_v, g_agg_m, g_agg_v, g_lp, g_lp_next) -> None:
+        """Backward of node_layer (csrc/node_layer_bwd.cu): writes g_h, g_x [N,3], g_agg_x, g_trans_v [N,4], g_agg_m, g_agg_v;
+        accumulates parameter gradients into g_lp (this layer) and g_lp_next (the projections of the next layer)."""
+        N, B, A, Cn, Na = dims
+        check(self.lib.distegnn_node_layer_bwd(N, A, Cn, Na, flags, ptr(rowptr), ptr(h), ptr(vel), ptr(attr), ptr(agg_m),
+                                               ptr(agg_v), ptr(lp), ptr(lp_next), ptr(g_x_out), ptr(g_vsum), ptr(batch32),
+                                               ptr(g_h_out), ptr(g_P), ptr(g_Q), ptr(g_Hn), ptr(g_h), ptr(g_x),
+                                               ptr(g_agg_x), ptr(g_trans_v), ptr(g_agg_m), ptr(g_agg_v), ptr(g_lp),
+                                               ptr(g_lp_next), self._s(h)), "node_layer_bwd")
+        self.launches += 1 if N else 0
+
+    def embed_bwd(self, dims, node_feat, h0, lp0, g_h, g_P, g_Q, g_Hn, g_emb_wt, g_emb_b, g_lp0) -> None:
+        """Backward of embed: accumulates g_emb_wt [F,64], g_emb_b [64] and layer 0's projection gradients into g_lp0."""
+        N, B, F, A, Cn, Na = dims
+        check(self.lib.distegnn_embed_bwd(N, F, A, Cn, Na, ptr(node_feat), ptr(h0), ptr(lp0), ptr(g_h), ptr(g_P), ptr(g_Q),
+                                          ptr(g_Hn), ptr(g_emb_wt), ptr(g_emb_b), ptr(g_lp0), self._s(h0)), "embed_bwd")
+        self.launches += 1 if N else 0
+
     def virtual_update(self, dims, flags, vsum, Xv, Hv, lp, lp_next, G, init_loc_mean=None, init_hv0=None,
                        comm: "Optional[Comm]" = None) -> None:
         """Virtual-node update; with `comm` the same kernel first all-reduces vsum over the partitions (NVLink peer

@@ -62,10 +62,12 @@ def _compile(src, verbose, objdir=None, defs=None):
 
 
 def _link(lib, objs):
-    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "shared",
+    tmp = lib + ".tmp"                      # link aside, then rename: a snapshot of the tree never sees a half-written .so
+    p = subprocess.run([NVCC, *ARCH, "-shared", "-o", tmp, *objs, "-cudart", "shared",
                         "-Xlinker", "-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    os.replace(tmp, lib)
     return lib
 
 

@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
         for (int i = tid; i < C * H; i += NTHREADS) {
             const int c = i / H, n = i - c * H;
             float s = __ldg(a.mb1 + n);
+            // weights come straight from L2 (each is used by C rows only): keep 16 loads in flight per thread
+#pragma unroll 16
             for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.m1 + k * H + n), s);
+#pragma unroll 16
             for (int k = 0; k < H; ++k) s = fmaf(sAg[c * H + k], __ldg(a.m1 + (H + k) * H + n), s);
             sT[i] = silu(s);
         }
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
         for (int i = tid; i < C * H; i += NTHREADS, ++u) {
             const int c = i / H, n = i - c * H;
             float s = __ldg(a.mb2 + n);
+#pragma unroll 16
             for (int k = 0; k < H; ++k) s = fmaf(sT[c * H + k], __ldg(a.m2 + k * H + n), s);
             upd[u] = sHv[i] + s;
         }
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
     for (int i = tid; i < C * H; i += NTHREADS) {
         const int c = i / H, n = i - c * H;
         float s = __ldg(a.nvb1 + n);
+#pragma unroll 16
         for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.nv1v + k * H + n), s);
         for (int j = 0; j < C; ++j) s = fmaf(sM[j * C + c], __ldg(a.nv1m + j * H + n), s);
         a.G[(size_t)b * C * H + i] = s;

@@ -584,9 +584,10 @@ class FastEGNN(nn.Module):
 
 class _FastEGNNFunction(torch.autograd.Function):
     """Autograd node of the fused path.  forward = the sm_100a kernels (FastEGNN._run_saving); backward = per layer, in
-    reverse: virtual-node update and node stage (dense [N,64] layers: torch recompute + autograd, _dense_stages.py),
-    ONE packed all-reduce of the statistics' gradient (the reference's _AllReduce.backward, FastEGNN.py:19-21, issues
-    one per aggregate), then the hand-written real<->virtual and per-edge backward kernels (csrc/*_bwd.cu)."""
+    reverse: virtual-node update (per graph, [B,C,64]: torch recompute + autograd, _dense_stages.py), ONE packed
+    all-reduce of the statistics' gradient (the reference's _AllReduce.backward, FastEGNN.py:19-21, issues one per
+    aggregate), then the hand-written backward kernels of the per-node, real<->virtual and per-edge stages and of the
+    embedding prologue (csrc/*_bwd*.cu)."""
 
     @staticmethod
     def forward(ctx, model, be, dims, a, emb_wt, emb_b, hv0, *lps):
@@ -612,8 +613,6 @@ class _FastEGNNFunction(torch.autograd.Function):
         g_emb_wt, g_emb_b, g_hv0 = torch.zeros_like(emb_wt), torch.zeros_like(emb_b), torch.zeros_like(hv0)
         if L == 0:
             return (None, None, None, None, g_emb_wt, g_emb_b, g_hv0)
-        batch = a["data_batch"]
-        deg = (a["rowptr"][1:] - a["rowptr"][:-1]).clamp(min=1).to(torch.float32).unsqueeze(1)
         attr = a["attr"]
 
         def leaf(t):
@@ -645,27 +644,14 @@ class _FastEGNNFunction(torch.autograd.Function):
                 g_lps[i + 1] += r[4]
             if model.world_size > 1:                     # _AllReduce.backward (FastEGNN.py:19-21), one packed call
                 model._sync_virtual(g_vsum, be, st.get("comm"))
-            # ---- 2. node stage: (g_x', g_h', g_P', g_Q', g_Hn') -> g_h, g_x, g_agg_*, g_trans_v, parameter gradients -----
-            with torch.enable_grad():
-                hl, xl = leaf(S["h"]), leaf(S["x4"][:, :3])
-                axl, tvl = leaf(S["agg_x"][:, :3]), leaf(S["trans_v"][:, :3])
-                aml = None if last else leaf(S["agg_m"])
-                avl = None if last else leaf(S["agg_v"])
-                lpl = leaf(lp)
-                lpn = None if last else leaf(lp_next)
-                xn, hn, Pn, Qn, Hnn = ds.node_stage(hl, xl, a["node_vel"], attr, aml, axl, avl, tvl, deg,
-                                                    ds.field_views(lpl, A, Cn, Na),
-                                                    None if last else ds.field_views(lpn, A, Cn, Na))
-                ins = [hl, xl, axl, tvl, lpl] + ([] if last else [aml, avl, lpn])
-                r = grads([xn, hn, Pn, Qn, Hnn], [g_x + g_vsum[batch, 0:3], g_h, g_P, g_Q, g_Hn], ins)
-            g_h_i, g_x_i = r[0], r[1]
-            g_agg_x, g_trans_v = zeros(N, 4), zeros(N, 4)
-            g_agg_x[:, :3], g_trans_v[:, :3] = r[2], r[3]
-            g_lps[i] += r[4]
-            g_agg_m = g_agg_v = None
-            if not last:
-                g_agg_m, g_agg_v = r[5].contiguous(), r[6].contiguous()
-                g_lps[i + 1] += r[7]
+            # ---- 2. node stage (CUDA): (g_x', g_h', g_P', g_Q', g_Hn') -> g_h, g_x, g_agg_*, g_trans_v, parameter gradients ----
+            g_h_i, g_x_i = torch.empty(N, H, device=dev), torch.empty(N, 3, device=dev)
+            g_agg_x, g_trans_v = torch.empty(N, 4, device=dev), torch.empty(N, 4, device=dev)
+            g_agg_m = None if last else torch.empty(N, H, device=dev)
+            g_agg_v = None if last else torch.empty(N, H, device=dev)
+            be.node_layer_bwd((N, B, A, Cn, Na), S["flags"], a["rowptr"], st["batch32"], S["h"], a["node_vel"], attr,
+                              S["agg_m"], S["agg_v"], lp, lp_next, g_x, g_vsum, g_h, g_P, g_Q, g_Hn, g_h_i, g_x_i,
+                              g_agg_x, g_trans_v, g_agg_m, g_agg_v, g_lps[i], None if last else g_lps[i + 1])
             # ---- 3. real<->virtual stage (CUDA) ------------------------------------------------------------------------
             wT = be.virtual_bwd_prepare(A, Cn, Na, lp)           # operand images of the stage's weights for the tensor cores
             g_Hn_i, g_xv = torch.empty(N, H, device=dev), torch.empty(N, 4, device=dev)
@@ -688,12 +674,7 @@ class _FastEGNNFunction(torch.autograd.Function):
             r = grads([Hv0o, G0], [g_Hv, g_G], [hv0l, lp0])
         g_hv0 += r[0]
         g_lps[0] += r[1]
-        # ---- embedding + layer-0 projections ----------------------------------------------------------------------------------
-        with torch.enable_grad():
-            wl, bl, lp0 = leaf(emb_wt), leaf(emb_b), leaf(layers[0])
-            h0, P0, Q0, Hn0 = ds.embed_stage(a["node_feat"], wl, bl, ds.field_views(lp0, A, Cn, Na))
-            r = grads([h0, P0, Q0, Hn0], [g_h, g_P, g_Q, g_Hn], [wl, bl, lp0])
-        g_emb_wt += r[0]
-        g_emb_b += r[1]
-        g_lps[0] += r[2]
+        # ---- embedding + layer-0 projections (CUDA) ----------------------------------------------------------------------------
+        be.embed_bwd((N, B, model.node_feat_nf, A, Cn, Na), a["node_feat"], st["layers"][0]["h"], layers[0], g_h, g_P, g_Q,
+                     g_Hn, g_emb_wt, g_emb_b, g_lps[0])
         return (None, None, None, None, g_emb_wt, g_emb_b, g_hv0, *g_lps)

@@ -279,6 +279,27 @@ DISTEGNN_API int distegnn_node_layer_fwd(int64_t n_nodes, int n_graphs, int A, i
                             const float *next_layer_params, float *h_out, float *x4_out, float *P,
                             float *Q, float *Hn, float *node_loc_out, float *vsum, void *stream);
 
+/* Backward of distegnn_node_layer_fwd and of the embedding prologue (in the reference: autograd through
+ * models/FastEGNN.py:177-183, 203-217, 302) — fp32 FMA tile GEMMs, everything recomputed from N-sized tensors.
+ * Upstream: g_x_out [N,3] (w.r.t. x'), g_vsum [B,K] (optional; its [b,0:3] entries add to g_x' of the nodes of graph b —
+ * x' feeds the next layer's Σ x'), g_h_out / g_P / g_Q / g_Hn [N,64] (w.r.t. h' and the next layer's projections; NULL with
+ * FLAG_LAST).  WRITTEN: g_h [N,64], g_x [N,3], g_agg_x / g_trans_v [N,4], g_agg_m / g_agg_v [N,64] (not with FLAG_LAST).
+ * ACCUMULATED: fields L_W, L_B, L_W3, L_B3, N_W1, N_B1, N_W2, N_B2 of g_layer_params and E_W1A, E_B1, E_W1B, V_W1H of
+ * g_next_layer_params (parameter-layout buffers).  distegnn_embed_bwd: h0 = the forward's h of layer 0; accumulates
+ * g_emb_wt [F][64], g_emb_b [64] and the same four projection fields of layer 0's gradient block. */
+DISTEGNN_API int distegnn_node_layer_bwd(int64_t n_nodes, int A, int C, int Na, unsigned flags, const int32_t *rowptr,
+                                         const float *h, const float *node_vel, const float *node_attr,
+                                         const float *agg_m, const float *agg_v, const float *layer_params,
+                                         const float *next_layer_params, const float *g_x_out, const float *g_vsum,
+                                         const int32_t *batch32, const float *g_h_out, const float *g_P, const float *g_Q,
+                                         const float *g_Hn, float *g_h, float *g_x, float *g_agg_x, float *g_trans_v,
+                                         float *g_agg_m, float *g_agg_v, float *g_layer_params,
+                                         float *g_next_layer_params, void *stream);
+DISTEGNN_API int distegnn_embed_bwd(int64_t n_nodes, int F, int A, int C, int Na, const float *node_feat, const float *h0,
+                                    const float *layer0_params, const float *g_h, const float *g_P, const float *g_Q,
+                                    const float *g_Hn, float *g_emb_wt, float *g_emb_b, float *g_layer0_params,
+                                    void *stream);
+
 /* ---- virtual-node sync: packed SUM all-reduce over NVLink peer memory ------------------------------------------------
  * Replaces weighted_average_reduce / _AllReduce (models/FastEGNN.py:10-43, 310-319; call sites :195-197, 225-227,
  * 259-261 — six NCCL calls behind host syncs per layer) with ONE exchange of the packed statistics vsum [B,K] per layer.

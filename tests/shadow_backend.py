@@ -190,6 +190,55 @@ class ShadowBackend:
     def virtual_bwd_prepare(self, A, Cn, Na, lp):
         return None
 
+    def node_layer_bwd(self, dims, flags, rowptr, batch32, h, vel, attr, agg_m, agg_v, lp, lp_next, g_x_out, g_vsum,
+                       g_h_out, g_P, g_Q, g_Hn, g_h, g_x, g_agg_x, g_trans_v, g_agg_m, g_agg_v, g_lp, g_lp_next):
+        """torch.autograd through distegnn_b200._dense_stages.node_stage: the contract of distegnn_node_layer_bwd."""
+        from distegnn_b200 import _dense_stages as ds
+        N, B, A, C, Na = dims
+        last = bool(flags & _lib.FLAG_LAST)
+        deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(h.dtype).unsqueeze(1)
+        leaf = lambda t: t.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            hl, lpl = leaf(h), leaf(lp)
+            xl, axl, tvl = (torch.zeros(N, 3, dtype=h.dtype, device=h.device).requires_grad_(True) for _ in range(3))
+            aml, avl, lpn = (None, None, None) if last else (leaf(agg_m), leaf(agg_v), leaf(lp_next))
+            xn, hn, Pn, Qn, Hnn = ds.node_stage(hl, xl, vel, attr if Na else None, aml, axl, avl, tvl, deg,
+                                                ds.field_views(lpl, A, C, Na),
+                                                None if last else ds.field_views(lpn, A, C, Na))
+            gx = g_x_out if g_vsum is None else g_x_out + g_vsum[batch32.long(), 0:3]
+            outs, gouts = [xn], [gx]
+            for o, g in ((hn, g_h_out), (Pn, g_P), (Qn, g_Q), (Hnn, g_Hn)):
+                if o is not None and g is not None:
+                    outs.append(o)
+                    gouts.append(g)
+            ins = [hl, xl, axl, tvl, lpl] + ([] if last else [aml, avl, lpn])
+            r = torch.autograd.grad(outs, ins, gouts, allow_unused=True)
+            r = [torch.zeros_like(i) if g is None else g for g, i in zip(r, ins)]
+        g_h.copy_(r[0])
+        g_x.copy_(r[1])
+        g_agg_x.zero_(); g_agg_x[:, :3] = r[2]
+        g_trans_v.zero_(); g_trans_v[:, :3] = r[3]
+        g_lp += r[4]
+        if not last:
+            g_agg_m.copy_(r[5])
+            g_agg_v.copy_(r[6])
+            g_lp_next += r[7]
+
+    def embed_bwd(self, dims, node_feat, h0, lp0, g_h, g_P, g_Q, g_Hn, g_emb_wt, g_emb_b, g_lp0):
+        from distegnn_b200 import _dense_stages as ds
+        N, B, Fn, A, C, Na = dims
+        with torch.enable_grad():
+            wl = torch.zeros(Fn, H, dtype=h0.dtype, device=h0.device).requires_grad_(True)
+            bl = torch.zeros(H, dtype=h0.dtype, device=h0.device).requires_grad_(True)
+            lp = lp0.detach().clone().requires_grad_(True)
+            # h0 = feat·W + b is linear in (W, b): evaluate the stage around the saved h0
+            hh = h0.detach() + node_feat @ wl + bl
+            P, Q, Hn = ds.projections(hh, ds.field_views(lp, A, C, Na))
+            r = torch.autograd.grad([hh, P, Q, Hn], [wl, bl, lp], [g_h, g_P, g_Q, g_Hn], allow_unused=True)
+        g_emb_wt += r[0]
+        g_emb_b += r[1]
+        g_lp0 += r[2]
+
     def virtual_layer_bwd(self, dims, flags, batch32, x4, Hn, Xv, G, lp, wT, g_agg_v, g_trans_v, g_vsum, g_Hn, g_xv,
                           g_G, g_Xv, g_lp):
         from tests import shadow_autograd as sa

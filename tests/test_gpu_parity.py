@@ -1280,3 +1280,87 @@ def test_split_large_graph_on_device_kmeans_and_random():
             he = set(zip(host[r]["edge_index"][0].tolist(), host[r]["edge_index"][1].tolist()))
             ge, E = _csr_edge_set(mine[r]["edge_index"])
             assert len(ge ^ he) <= max(2, int(2e-5 * len(he))), (mode, r, len(ge ^ he))     # pairs within an ulp of r
+
+
+# ---- f-1: backward of the per-node stage and of the embedding prologue (csrc/node_layer_bwd.cu) ---------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("Na,last,N", [(2, False, 5_003), (0, False, 300), (2, True, 1_111), (0, False, 128)])
+def test_node_stage_backward(Na, last, N):
+    """distegnn_node_layer_bwd against float64 autograd through the stage's torch restatement (tests/shadow_backend.py):
+    every data gradient and every parameter-gradient field, isolated nodes and a ragged last tile included."""
+    from distegnn_b200.backend import cuda_backend
+    be, sh = cuda_backend(), ShadowBackend()
+    A, C, B = 2, 3, 2
+    g = torch.Generator().manual_seed(N + Na)
+    sd = orc.init_state_dict(3, Na, A, 64, C, 2, seed=2, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=3, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=2), sd)
+    pk = m._packed_params(dev())
+    lp, lpn = pk["layers"][0], pk["layers"][1]
+    K = 4 + 3 * C + 64 * C
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    deg = torch.randint(0, 6, (N,), generator=g)
+    rowptr = torch.zeros(N + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
+    batch32 = torch.sort(torch.randint(0, B, (N,), generator=g)).values.to(torch.int32)
+    t = dict(h=rnd(N, 64), vel=rnd(N, 3), attr=rnd(N, Na) if Na else None, agg_m=rnd(N, 64) * 3, agg_v=rnd(N, 64),
+             g_x=rnd(N, 3), g_vsum=rnd(B, K), g_h=rnd(N, 64), g_P=rnd(N, 64), g_Q=rnd(N, 64), g_Hn=rnd(N, 64))
+    flags = _lib.FLAG_LAST if last else 0
+    total = lp.numel()
+
+    def run(backend, dt, device):
+        c = lambda v: None if v is None else v.to(device=device, dtype=dt)
+        o = dict(g_h=torch.empty(N, 64, dtype=dt, device=device), g_x=torch.empty(N, 3, dtype=dt, device=device),
+                 g_agg_x=torch.empty(N, 4, dtype=dt, device=device), g_trans_v=torch.empty(N, 4, dtype=dt, device=device),
+                 g_agg_m=torch.zeros(N, 64, dtype=dt, device=device), g_agg_v=torch.zeros(N, 64, dtype=dt, device=device),
+                 g_lp=torch.zeros(total, dtype=dt, device=device), g_lpn=torch.zeros(total, dtype=dt, device=device))
+        backend.node_layer_bwd((N, B, A, C, Na), flags, rowptr.to(device), batch32.to(device), c(t["h"]), c(t["vel"]),
+                               c(t["attr"]), None if last else c(t["agg_m"]), None if last else c(t["agg_v"]),
+                               lp.to(device=device, dtype=dt), None if last else lpn.to(device=device, dtype=dt),
+                               c(t["g_x"]), c(t["g_vsum"]), None if last else c(t["g_h"]), None if last else c(t["g_P"]),
+                               None if last else c(t["g_Q"]), None if last else c(t["g_Hn"]), o["g_h"], o["g_x"],
+                               o["g_agg_x"], o["g_trans_v"], None if last else o["g_agg_m"], None if last else o["g_agg_v"],
+                               o["g_lp"], None if last else o["g_lpn"])
+        return o
+    got = run(be, torch.float32, dev())
+    torch.cuda.synchronize()
+    want = run(sh, torch.float64, torch.device("cpu"))
+    worst = {}
+    for k in want:
+        a_, b_ = got[k].cpu().double(), want[k]
+        if k in ("g_agg_x", "g_trans_v"):
+            a_, b_ = a_[:, :3], b_[:, :3]
+        den = float(b_.abs().max())
+        if den == 0.0:
+            assert float(a_.abs().max()) == 0.0, k
+            continue
+        worst[k] = float((a_ - b_).abs().max()) / den
+        assert worst[k] <= 2e-5, (k, worst[k])
+    print(f"node stage backward Na={Na} last={last} N={N}: " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F,N", [(3, 4_001), (1, 77), (16, 1_000)])
+def test_embed_backward(F, N):
+    from distegnn_b200.backend import cuda_backend
+    be, sh = cuda_backend(), ShadowBackend()
+    A, C, Na, B = 2, 5, 0, 1
+    g = torch.Generator().manual_seed(F)
+    sd = orc.init_state_dict(F, Na, A, 64, C, 1, seed=3)
+    m = cuda_model(dict(node_feat_nf=F, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=1), sd)
+    lp0 = m._packed_params(dev())["layers"][0]
+    feat, h0 = torch.randn(N, F, generator=g), torch.randn(N, 64, generator=g)
+    gs = [torch.randn(N, 64, generator=g) for _ in range(4)]
+
+    def run(backend, dt, device):
+        c = lambda v: v.to(device=device, dtype=dt)
+        o = (torch.zeros(F, 64, dtype=dt, device=device), torch.zeros(64, dtype=dt, device=device),
+             torch.zeros(lp0.numel(), dtype=dt, device=device))
+        backend.embed_bwd((N, B, F, A, C, Na), c(feat), c(h0), c(lp0), *[c(x) for x in gs], *o)
+        return o
+    got = run(be, torch.float32, dev())
+    torch.cuda.synchronize()
+    want = run(sh, torch.float64, torch.device("cpu"))
+    for a_, b_, name in zip(got, want, ("g_emb_wt", "g_emb_b", "g_lp0")):
+        e = float((a_.cpu().double() - b_).abs().max() / b_.abs().max())
+        print(f"embed backward F={F} N={N} {name}: rel err {e:.1e}")
+        assert e <= 2e-5
