@@ -45,6 +45,7 @@ SIGNATURES = {
     "distegnn_virtual_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
     "distegnn_node_layer_fwd": [_i64, _i32, _i32, _i32, _i32, _u32] + [_vp] * 20,
     "distegnn_virtual_update_fwd": [_i32, _i32, _i32, _i32, _u32] + [_vp] * 10,
+    "distegnn_virtual_update_bwd": [_i32, _i32, _i32, _i32, _u32] + [_vp] * 14,
     "distegnn_node_layer_bwd": [_i64, _i32, _i32, _i32, _u32] + [_vp] * 24,
     "distegnn_embed_bwd": [_i64, _i32, _i32, _i32, _i32] + [_vp] * 11,
     "distegnn_comm_handle_bytes": [],

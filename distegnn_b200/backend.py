@@ -181,6 +181,15 @@ class CudaBackend:
               "virtual_update_fwd")
         self.launches += 1 if B else 0
 
+    def virtual_update_bwd(self, dims, flags, vsum, Xv, Hv, lp, lp_next, g_Xn, g_Hn, g_G, g_vsum, g_Xv, g_Hv, g_lp,
+                           g_lp_next) -> None:
+        """Backward of virtual_update (csrc/virtual_update.cu): writes g_vsum, g_Xv, g_Hv; accumulates into g_lp / g_lp_next."""
+        B, A, Cn, Na = dims
+        check(self.lib.distegnn_virtual_update_bwd(B, A, Cn, Na, flags, ptr(vsum), ptr(Xv), ptr(Hv), ptr(lp), ptr(lp_next),
+                                                   ptr(g_Xn), ptr(g_Hn), ptr(g_G), ptr(g_vsum), ptr(g_Xv), ptr(g_Hv),
+                                                   ptr(g_lp), ptr(g_lp_next), self._s(vsum)), "virtual_update_bwd")
+        self.launches += 1 if B else 0
+
     def allreduce_packed(self, comm: "Comm", buf: Tensor) -> None:
         """In-place SUM of `buf` over the partitions through the communicator's peer-mapped segments."""
         check(self.lib.distegnn_allreduce_packed(comm.handle, ptr(buf), buf.numel(), self._s(buf)), "allreduce_packed")

@@ -584,10 +584,10 @@ class FastEGNN(nn.Module):
 
 class _FastEGNNFunction(torch.autograd.Function):
     """Autograd node of the fused path.  forward = the sm_100a kernels (FastEGNN._run_saving); backward = per layer, in
-    reverse: virtual-node update (per graph, [B,C,64]: torch recompute + autograd, _dense_stages.py), ONE packed
-    all-reduce of the statistics' gradient (the reference's _AllReduce.backward, FastEGNN.py:19-21, issues one per
-    aggregate), then the hand-written backward kernels of the per-node, real<->virtual and per-edge stages and of the
-    embedding prologue (csrc/*_bwd*.cu)."""
+    reverse: virtual-node update, ONE packed all-reduce of the statistics' gradient (the reference's _AllReduce.backward,
+    FastEGNN.py:19-21, issues one per aggregate), per-node stage, real<->virtual stage, per-edge stage, and finally the
+    initial virtual state and the embedding prologue — every one a hand-written kernel behind the C ABI (csrc/*bwd*.cu,
+    csrc/virtual_update.cu); torch only adds three gradient tensors per layer."""
 
     @staticmethod
     def forward(ctx, model, be, dims, a, emb_wt, emb_b, hv0, *lps):
@@ -600,7 +600,6 @@ class _FastEGNNFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_Xv_out):
-        from . import _dense_stages as ds
         model, be, a, st = ctx.model, ctx.be, ctx.a, ctx.st
         N, E, B, K = ctx.dims
         A, Cn, Na = model.edge_attr_nf, model.virtual_channels, model.node_attr_nf
@@ -614,15 +613,6 @@ class _FastEGNNFunction(torch.autograd.Function):
         if L == 0:
             return (None, None, None, None, g_emb_wt, g_emb_b, g_hv0)
         attr = a["attr"]
-
-        def leaf(t):
-            return t.detach().requires_grad_(True)
-
-        def grads(outs, gouts, ins):
-            pairs = [(o, g) for o, g in zip(outs, gouts) if o is not None and g is not None]
-            res = torch.autograd.grad([o for o, _ in pairs], ins, [g for _, g in pairs], allow_unused=True)
-            return [torch.zeros_like(i) if r is None else r for r, i in zip(res, ins)]
-
         g_x = g_out.contiguous().to(torch.float32) if g_out is not None else zeros(N, 3)
         g_Xv = g_Xv_out.contiguous().to(torch.float32) if g_Xv_out is not None else zeros(B, 3, Cn)
         g_Hv = g_G = g_h = g_P = g_Q = g_Hn = None
@@ -630,18 +620,11 @@ class _FastEGNNFunction(torch.autograd.Function):
             S = st["layers"][i]
             last = i == L - 1
             lp, lp_next = layers[i], (None if last else layers[i + 1])
-            # ---- 1. virtual-node update: (g_Xv', g_Hv', g_G') -> g_vsum, g_Xv, g_Hv, parameter gradients ----------------
-            with torch.enable_grad():
-                vs, Xl, Hl, lpl = leaf(S["vsum"]), leaf(S["Xv"]), leaf(S["Hv"]), leaf(lp)
-                lpn = None if last else leaf(lp_next)
-                Xn, Hvn, Gn = ds.virtual_update_stage(vs, Xl, Hl, ds.field_views(lpl, A, Cn, Na),
-                                                      None if last else ds.field_views(lpn, A, Cn, Na), False, Cn)
-                ins = [vs, Xl, Hl, lpl] + ([] if last else [lpn])
-                r = grads([Xn, Hvn, Gn], [g_Xv, g_Hv, g_G], ins)
-            g_vsum, g_Xv_i, g_Hv_i = r[0].contiguous(), r[1], r[2]
-            g_lps[i] += r[3]
-            if not last:
-                g_lps[i + 1] += r[4]
+            # ---- 1. virtual-node update (CUDA): (g_Xv', g_Hv', g_G') -> g_vsum, g_Xv, g_Hv, parameter gradients -------------
+            g_vsum, g_Xv_i = torch.empty(B, K, device=dev), torch.empty(B, 3, Cn, device=dev)
+            g_Hv_i = None if last else torch.empty(B, Cn, H, device=dev)
+            be.virtual_update_bwd((B, A, Cn, Na), S["flags"] & ~_lib.FLAG_NORMALIZE, S["vsum"], S["Xv"], S["Hv"], lp, lp_next,
+                                  g_Xv, g_Hv, g_G, g_vsum, g_Xv_i, g_Hv_i, g_lps[i], None if last else g_lps[i + 1])
             if model.world_size > 1:                     # _AllReduce.backward (FastEGNN.py:19-21), one packed call
                 model._sync_virtual(g_vsum, be, st.get("comm"))
             # ---- 2. node stage (CUDA): (g_x', g_h', g_P', g_Q', g_Hn') -> g_h, g_x, g_agg_*, g_trans_v, parameter gradients ----
@@ -665,15 +648,13 @@ class _FastEGNNFunction(torch.autograd.Function):
             g_x = g_x_i + g_xv[:, :3] + g_x4e[:, :3]
             g_h, g_P, g_Q, g_Hn = g_h_i, g_P_i, g_Q_i, g_Hn_i
             g_Xv, g_Hv, g_G = g_Xv_acc, g_Hv_i, g_G_i
-        # ---- initial virtual state: G_0 = f(Hv_0 = hv0, X_0 = loc_mean, x̄_0; layer-0 parameters) -------------------------
-        with torch.enable_grad():
-            hv0l, lp0 = leaf(hv0), leaf(layers[0])
-            Xv0 = a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn)
-            Hv0 = hv0l.unsqueeze(0).expand(B, Cn, H)
-            _, Hv0o, G0 = ds.virtual_update_stage(st["vsum_init"], Xv0, Hv0, None, ds.field_views(lp0, A, Cn, Na), True, Cn)
-            r = grads([Hv0o, G0], [g_Hv, g_G], [hv0l, lp0])
-        g_hv0 += r[0]
-        g_lps[0] += r[1]
+        # ---- initial virtual state (CUDA): G_0 = f(Hv_0 = hv0, X_0 = loc_mean, x̄_0; layer-0 parameters) ---------------------
+        Xv0 = a["loc_mean"].unsqueeze(-1).expand(B, 3, Cn).contiguous()
+        Hv0 = hv0.unsqueeze(0).expand(B, Cn, H).contiguous()
+        g_Hv0 = torch.empty(B, Cn, H, device=dev)
+        be.virtual_update_bwd((B, A, Cn, Na), _lib.FLAG_INIT, st["vsum_init"], Xv0, Hv0, None, layers[0], None, g_Hv, g_G,
+                              torch.empty(B, K, device=dev), torch.empty(B, 3, Cn, device=dev), g_Hv0, None, g_lps[0])
+        g_hv0 += g_Hv0.sum(0)                                # virtual_node_feat is shared by the graphs of the batch
         # ---- embedding + layer-0 projections (CUDA) ----------------------------------------------------------------------------
         be.embed_bwd((N, B, model.node_feat_nf, A, Cn, Na), a["node_feat"], st["layers"][0]["h"], layers[0], g_h, g_P, g_Q,
                      g_Hn, g_emb_wt, g_emb_b, g_lps[0])

@@ -348,6 +348,17 @@ DISTEGNN_API int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na,
                                 const float *next_layer_params, float *G, const float *init_loc_mean,
                                 const float *init_hv0, void *comm, void *stream);
 
+/* Backward of distegnn_virtual_update_fwd (per graph; in the reference: autograd through models/FastEGNN.py:193-199,
+ * 222-234, 258-264).  vsum = the SUMMED statistics the forward consumed, Xv / Hv = the forward's inputs (with FLAG_INIT: the
+ * initial loc_mean / virtual_node_feat broadcasts).  Upstream g_Xn [B,3,C], g_Hn, g_G [B,C,64] (NULL = zero).  WRITTEN:
+ * g_vsum [B,K] (entry 3, the node count, gets 0), g_Xv [B,3,C], g_Hv [B,C,64] (not with FLAG_LAST).  ACCUMULATED: M_W1, M_B1,
+ * M_W2, M_B2 of g_layer_params (regular layers) and V_W1V, V_W1M, V_B1 of g_next_layer_params. */
+DISTEGNN_API int distegnn_virtual_update_bwd(int n_graphs, int A, int C, int Na, unsigned flags, const float *vsum,
+                                             const float *Xv, const float *Hv, const float *layer_params,
+                                             const float *next_layer_params, const float *g_Xn, const float *g_Hn,
+                                             const float *g_G, float *g_vsum, float *g_Xv, float *g_Hv,
+                                             float *g_layer_params, float *g_next_layer_params, void *stream);
+
 /* ---- loss side of the training step -------------------------------------------------------------------
  * Replaces utils/train.py:98-147: node-count weighted MSE (:98-110), the MMD regulariser between the virtual
  * coordinates and S = samples·C sampled target positions per graph (:119-147, kernel k(x,y) = exp(−‖x−y‖₂/(2σ²)), :11-14)

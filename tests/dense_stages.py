@@ -1,16 +1,10 @@
-"""Differentiable torch forms of the per-NODE and per-GRAPH dense stages — used ONLY by the backward pass.
+"""Differentiable torch forms of the per-NODE and per-GRAPH dense stages — TEST INFRASTRUCTURE.
 
-Scope: the forward pass never touches this file — every stage runs in the hand-written kernels behind
-the C ABI.  In the backward pass the two stages whose reference implementation blows up memory and time — the
-per-edge stage (E rows) and the real<->virtual stage (N·C rows) — are hand-written CUDA as well
-(csrc/edge_layer_bwd.cu, csrc/virtual_layer_bwd.cu).  What remains are plain dense layers on [N,64] / [B,C,64]
-matrices (node MLP, velocity head, the P/Q/Hn projections, the virtual-node update, the embedding): for those the
-backward recomputes the stage here with torch matmuls (cuBLAS) and lets torch.autograd differentiate it.  A fused
-backward kernel for them is the next step of SURVEY §8 f-1; they are N-sized, not E-sized, so nothing large is
-materialised.
-
-Each function restates what the corresponding C-ABI kernel computes (same decomposition: P/Q/Hn split of the first
-MLP layers, SUMS instead of means, packed vsum), with the reference lines it stands for.
+Restates what the node / virtual-update / embedding kernels compute (same decomposition: P/Q/Hn split of the first MLP
+layers, SUMS instead of means, packed vsum), with the reference lines each stands for.  Until round 2 the backward pass of
+the product recomputed these stages here and let torch.autograd (cuBLAS) differentiate them; they are now hand-written
+kernels (csrc/node_layer_bwd.cu, csrc/virtual_update.cu), and this file only backs the torch stand-in backend
+(tests/shadow_backend.py) those kernels are tested against.  Nothing in the package imports it.
 """
 from __future__ import annotations
 
@@ -19,7 +13,7 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
-from . import _lib
+from distegnn_b200 import _lib
 
 Tensor = torch.Tensor
 H = _lib.HIDDEN

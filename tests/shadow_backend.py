@@ -193,7 +193,7 @@ class ShadowBackend:
     def node_layer_bwd(self, dims, flags, rowptr, batch32, h, vel, attr, agg_m, agg_v, lp, lp_next, g_x_out, g_vsum,
                        g_h_out, g_P, g_Q, g_Hn, g_h, g_x, g_agg_x, g_trans_v, g_agg_m, g_agg_v, g_lp, g_lp_next):
         """torch.autograd through distegnn_b200._dense_stages.node_stage: the contract of distegnn_node_layer_bwd."""
-        from distegnn_b200 import _dense_stages as ds
+        from tests import dense_stages as ds
         N, B, A, C, Na = dims
         last = bool(flags & _lib.FLAG_LAST)
         deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(h.dtype).unsqueeze(1)
@@ -224,8 +224,34 @@ class ShadowBackend:
             g_agg_v.copy_(r[6])
             g_lp_next += r[7]
 
+    def virtual_update_bwd(self, dims, flags, vsum, Xv, Hv, lp, lp_next, g_Xn, g_Hn, g_G, g_vsum, g_Xv, g_Hv, g_lp, g_lp_next):
+        """torch.autograd through _dense_stages.virtual_update_stage: the contract of distegnn_virtual_update_bwd."""
+        from tests import dense_stages as ds
+        B, A, C, Na = dims
+        init, last = bool(flags & _lib.FLAG_INIT), bool(flags & _lib.FLAG_LAST)
+        leaf = lambda t: t.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            vs, Xl = leaf(vsum), leaf(Xv)
+            Hl = None if last else leaf(Hv)
+            lpl = None if (init or lp is None) else leaf(lp)
+            lpn = None if last else leaf(lp_next)
+            Xn, Hn, Gn = ds.virtual_update_stage(vs, Xl, Hl, None if lpl is None else ds.field_views(lpl, A, C, Na),
+                                                 None if last else ds.field_views(lpn, A, C, Na), init, C)
+            pairs = [(o, g) for o, g in ((Xn, g_Xn), (Hn, g_Hn), (Gn, g_G)) if o is not None and g is not None and o.requires_grad]
+            ins = [t for t in (vs, Xl, Hl, lpl, lpn) if t is not None]
+            r = torch.autograd.grad([o for o, _ in pairs], ins, [g for _, g in pairs], allow_unused=True) if pairs else [None] * len(ins)
+            r = {id(i): (torch.zeros_like(i) if g is None else g) for g, i in zip(r, ins)}
+        g_vsum.copy_(r[id(vs)])
+        g_Xv.copy_(r[id(Xl)])
+        if Hl is not None and g_Hv is not None:
+            g_Hv.copy_(r[id(Hl)])
+        if lpl is not None:
+            g_lp += r[id(lpl)]
+        if lpn is not None:
+            g_lp_next += r[id(lpn)]
+
     def embed_bwd(self, dims, node_feat, h0, lp0, g_h, g_P, g_Q, g_Hn, g_emb_wt, g_emb_b, g_lp0):
-        from distegnn_b200 import _dense_stages as ds
+        from tests import dense_stages as ds
         N, B, Fn, A, C, Na = dims
         with torch.enable_grad():
             wl = torch.zeros(Fn, H, dtype=h0.dtype, device=h0.device).requires_grad_(True)

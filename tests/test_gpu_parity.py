@@ -1364,3 +1364,48 @@ def test_embed_backward(F, N):
         e = float((a_.cpu().double() - b_).abs().max() / b_.abs().max())
         print(f"embed backward F={F} N={N} {name}: rel err {e:.1e}")
         assert e <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,B,mode", [(8, 1, "mid"), (5, 3, "mid"), (3, 2, "last"), (16, 2, "init"), (1, 4, "mid")])
+def test_virtual_update_backward(C, B, mode):
+    """distegnn_virtual_update_bwd against float64 autograd through the stage's torch restatement."""
+    from distegnn_b200.backend import cuda_backend
+    be, sh = cuda_backend(), ShadowBackend()
+    A, Na = 2, 0
+    K = 4 + 3 * C + 64 * C
+    g = torch.Generator().manual_seed(C * 10 + B)
+    sd = orc.init_state_dict(2, Na, A, 64, C, 2, seed=6, coord_gain=1.0)
+    m = cuda_model(dict(node_feat_nf=2, node_attr_nf=Na, edge_attr_nf=A, virtual_channels=C, n_layers=2), sd)
+    pk = m._packed_params(dev())
+    lp, lpn = pk["layers"][0], pk["layers"][1]
+    flags = {"mid": 0, "last": _lib.FLAG_LAST, "init": _lib.FLAG_INIT}[mode]
+    vs = torch.randn(B, K, generator=g)
+    vs[:, 3] = torch.tensor([500.0 + 13 * b for b in range(B)])
+    t = dict(vs=vs, Xv=torch.randn(B, 3, C, generator=g), Hv=torch.randn(B, C, 64, generator=g),
+             gX=torch.randn(B, 3, C, generator=g), gH=torch.randn(B, C, 64, generator=g), gG=torch.randn(B, C, 64, generator=g))
+    last, init = mode == "last", mode == "init"
+
+    def run(backend, dt, device):
+        c = lambda v: v.to(device=device, dtype=dt)
+        o = dict(g_vsum=torch.zeros(B, K, dtype=dt, device=device), g_Xv=torch.zeros(B, 3, C, dtype=dt, device=device),
+                 g_Hv=torch.zeros(B, C, 64, dtype=dt, device=device), g_lp=torch.zeros(lp.numel(), dtype=dt, device=device),
+                 g_lpn=torch.zeros(lp.numel(), dtype=dt, device=device))
+        backend.virtual_update_bwd((B, A, C, Na), flags, c(t["vs"]), c(t["Xv"]), c(t["Hv"]), None if init else c(lp),
+                                   None if last else c(lpn), c(t["gX"]), None if last else c(t["gH"]),
+                                   None if last else c(t["gG"]), o["g_vsum"], o["g_Xv"], None if last else o["g_Hv"],
+                                   None if init else o["g_lp"], None if last else o["g_lpn"])
+        return o
+    got = run(be, torch.float32, dev())
+    torch.cuda.synchronize()
+    want = run(sh, torch.float64, torch.device("cpu"))
+    worst = {}
+    for k in want:
+        a_, b_ = got[k].cpu().double(), want[k]
+        den = float(b_.abs().max())
+        if den == 0.0:
+            assert float(a_.abs().max()) == 0.0, k
+            continue
+        worst[k] = float((a_ - b_).abs().max()) / den
+        assert worst[k] <= 2e-5, (k, worst[k])
+    print(f"virtual update backward C={C} B={B} {mode}: " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
