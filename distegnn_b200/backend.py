@@ -36,7 +36,9 @@ class CudaBackend:
     def build_csr(self, edge_index: Tensor, n_nodes: int, validate: bool = True
                   ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         """int64 COO -> int32 CSR by destination.  `validate`: read back the out-of-range counter (one host sync per
-        build; builds are cached per edge_index) and raise ValueError like the reference's index assert would."""
+        build; builds are cached per edge_index) and raise ValueError like the reference's index assert would;
+        validate="defer" hands the device counter back as a fifth value instead (the caller reads it together with the
+        data_batch counter after the embed kernel: one pipeline drain for both checks; ids are clamped meanwhile)."""
         E = int(edge_index.shape[1])
         dev = edge_index.device
         stream = self._s(edge_index)
@@ -51,6 +53,8 @@ class CudaBackend:
         check(self.lib.distegnn_build_csr(ptr(edge_index), n_nodes, E, ptr(rowptr), ptr(row), ptr(col),
                                           ptr(perm), ptr(ws), ws.numel(), ptr(bad), stream), "build_csr")
         self.launches += (5 if E else 1) + (1 if validate else 0)
+        if validate == "defer":
+            return rowptr, row, col, perm, (bad if E else None)
         if validate and E and int(bad.item()) != 0:
             raise ValueError(f"edge_index has {int(bad.item())} edge(s) with a node id outside [0, {n_nodes})")
         return rowptr, row, col, perm

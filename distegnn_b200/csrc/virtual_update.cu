@@ -27,9 +27,10 @@ struct VUpdArgs {
 };
 
 constexpr int VU_KMAX = 4 + 3 * DISTEGNN_MAX_CHANNELS + H * DISTEGNN_MAX_CHANNELS;
+constexpr int VU_THREADS = 512;          // one (channel, column) output per thread at C = 8: the kernel is pure latency
 
 template <bool SYNC>
-__global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs a, const CommDev cd) {
+__global__ void __launch_bounds__(VU_THREADS) virtual_update_kernel(const VUpdArgs a, const CommDev cd) {
     constexpr int MC = DISTEGNN_MAX_CHANNELS;
     __shared__ float sV[VU_KMAX];       // vsum[b,:] (summed over the partitions)
     __shared__ float sX[3 * MC];        // new Xv [3][C]
@@ -43,13 +44,13 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
     const bool init = a.flags & DISTEGNN_FLAG_INIT;
     const bool last = a.flags & DISTEGNN_FLAG_LAST;
     const bool zero = a.flags & DISTEGNN_FLAG_ZERO_VSUM;
-    for (int i = tid; i < a.K; i += NTHREADS) sV[i] = vg[i];
+    for (int i = tid; i < a.K; i += VU_THREADS) sV[i] = vg[i];
     __syncthreads();
     if (SYNC) comm_slot_allreduce(cd, b, sV, a.K);
     if (zero) {
-        for (int i = tid; i < a.K; i += NTHREADS) vg[i] = 0.f;
+        for (int i = tid; i < a.K; i += VU_THREADS) vg[i] = 0.f;
     } else if (SYNC) {
-        for (int i = tid; i < a.K; i += NTHREADS) vg[i] = sV[i];
+        for (int i = tid; i < a.K; i += VU_THREADS) vg[i] = sV[i];
     }
     const float* vs = sV;
     const float inv = 1.0f / fmaxf(vs[3], 1.0f);
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
         sZ[tid] = x - vs[tid / C] * inv;   // tid / C = spatial dim
     }
     if (last) return;
-    for (int i = tid; i < C * H; i += NTHREADS) {
+    for (int i = tid; i < C * H; i += VU_THREADS) {
         const float hv = (init && a.init_hv0) ? a.init_hv0[i] : a.Hv[(size_t)b * C * H + i];
         sHv[i] = hv;
         if (init && a.init_hv0) a.Hv[(size_t)b * C * H + i] = hv;
@@ -75,39 +76,36 @@ __global__ void __launch_bounds__(NTHREADS) virtual_update_kernel(const VUpdArgs
     }
     if (!init) {
         // Hv' = Hv + W2·SiLU(W1·[Hv; agg] + b1) + b2   (per channel; thread per (c, n))
-        for (int i = tid; i < C * H; i += NTHREADS) {
+        for (int i = tid; i < C * H; i += VU_THREADS) {
             const int c = i / H, n = i - c * H;
             float s = __ldg(a.mb1 + n);
-            // weights come straight from L2 (each is used by C rows only): keep 16 loads in flight per thread
-#pragma unroll 16
+            // weights come straight from L2 (each is used by C rows only); the 64-step loops are fully unrolled by the
+            // compiler, i.e. all loads of a row are in flight together
             for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.m1 + k * H + n), s);
-#pragma unroll 16
             for (int k = 0; k < H; ++k) s = fmaf(sAg[c * H + k], __ldg(a.m1 + (H + k) * H + n), s);
             sT[i] = silu(s);
         }
         __syncthreads();
-        float upd[(MC * H + NTHREADS - 1) / NTHREADS];
+        float upd[(MC * H + VU_THREADS - 1) / VU_THREADS];
         int u = 0;
-        for (int i = tid; i < C * H; i += NTHREADS, ++u) {
+        for (int i = tid; i < C * H; i += VU_THREADS, ++u) {
             const int c = i / H, n = i - c * H;
             float s = __ldg(a.mb2 + n);
-#pragma unroll 16
             for (int k = 0; k < H; ++k) s = fmaf(sT[c * H + k], __ldg(a.m2 + k * H + n), s);
             upd[u] = sHv[i] + s;
         }
         __syncthreads();
         u = 0;
-        for (int i = tid; i < C * H; i += NTHREADS, ++u) {
+        for (int i = tid; i < C * H; i += VU_THREADS, ++u) {
             sHv[i] = upd[u];
             a.Hv[(size_t)b * C * H + i] = upd[u];
         }
     }
     __syncthreads();
     // G[c][n] = Σ_k W1v_V[k][n]·Hv'[c][k] + Σ_j W1v_M[j][n]·m_X[j][c] + b1v[n]
-    for (int i = tid; i < C * H; i += NTHREADS) {
+    for (int i = tid; i < C * H; i += VU_THREADS) {
         const int c = i / H, n = i - c * H;
         float s = __ldg(a.nvb1 + n);
-#pragma unroll 16
         for (int k = 0; k < H; ++k) s = fmaf(sHv[c * H + k], __ldg(a.nv1v + k * H + n), s);
         for (int j = 0; j < C; ++j) s = fmaf(sM[j * C + c], __ldg(a.nv1m + j * H + n), s);
         a.G[(size_t)b * C * H + i] = s;
@@ -148,11 +146,11 @@ extern "C" int distegnn_virtual_update_fwd(int n_graphs, int A, int C, int Na, u
         DEGNN_CHECK_ARG(c->connected, "comm not connected (distegnn_comm_connect)");
         DEGNN_CHECK_ARG(n_graphs <= c->dev.max_slots && a.K <= c->dev.stride,
                         "comm capacity (max_slots, slot_floats) too small for [n_graphs, K]");
-        virtual_update_kernel<true><<<(unsigned)n_graphs, NTHREADS, 0, (cudaStream_t)stream>>>(a, c->dev);
+        virtual_update_kernel<true><<<(unsigned)n_graphs, VU_THREADS, 0, (cudaStream_t)stream>>>(a, c->dev);
     } else {
         CommDev none;
         none.world = 1; none.rank = 0;
-        virtual_update_kernel<false><<<(unsigned)n_graphs, NTHREADS, 0, (cudaStream_t)stream>>>(a, none);
+        virtual_update_kernel<false><<<(unsigned)n_graphs, VU_THREADS, 0, (cudaStream_t)stream>>>(a, none);
     }
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;

@@ -134,6 +134,7 @@ class _GraphCache:
         self.capacity = capacity
         self.entries: "OrderedDict[int, tuple]" = OrderedDict()
         self.builds = 0
+        self.pending = None                # device counter of the last build's out-of-range edge ids (read after embed)
 
     def get(self, backend, edge_index: Tensor, n_nodes: int, validate: bool = True):
         key = id(edge_index)
@@ -142,7 +143,8 @@ class _GraphCache:
             self.entries.move_to_end(key)
             return hit[3]
         ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
-        csr = backend.build_csr(ei, n_nodes, validate)
+        built = backend.build_csr(ei, n_nodes, "defer" if validate else False)
+        csr, self.pending = tuple(built[:4]), (built[4] if validate else None)     # counter of out-of-range ids, not yet read
         self.builds += 1
         self.entries[key] = (edge_index, edge_index._version, n_nodes, csr)
         while len(self.entries) > self.capacity:
@@ -369,8 +371,15 @@ class FastEGNN(nn.Module):
                                               and v[2] == N and v[3] == B)
 
     def _check_batch(self, counter: Optional[Tensor], data_batch: Tensor, N: int, B: int) -> None:
-        """Read the embed kernel's counter of unsorted / out-of-range data_batch entries (one host sync per distinct
-        data_batch tensor) and raise like the reference's scatter would on an out-of-range id."""
+        """Read the device-side validation counters — out-of-range edge ids of a CSR build that has just happened, and the
+        embed kernel's count of unsorted / out-of-range data_batch entries — in one pipeline drain, and raise like the
+        reference's index assert / scatter would.  Only when a new edge_index / data_batch tensor shows up."""
+        pend, self._graphs.pending = self._graphs.pending, None
+        if pend is not None:
+            bad_e = int(pend.item())
+            if bad_e:
+                self._graphs.entries.clear()
+                raise ValueError(f"edge_index has {bad_e} edge(s) with a node id outside [0, {N})")
         if counter is None:
             return
         bad = int(counter.item())

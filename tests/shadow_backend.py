@@ -50,6 +50,8 @@ class ShadowBackend:
         counts = torch.bincount(row64, minlength=n_nodes)
         rowptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=edge_index.device)
         rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        if validate == "defer":
+            return rowptr, row, col, perm.to(torch.int32), None
         return rowptr, row, col, perm.to(torch.int32)
 
     def gather_rows(self, src, perm):
