@@ -53,6 +53,7 @@ SIGNATURES = {
     "distegnn_comm_connect": [_vp, _vp],
     "distegnn_comm_set_timeout_ms": [_vp, _i64],
     "distegnn_comm_status": [_vp, C.POINTER(_i32)],
+    "distegnn_comm_disconnect": [_vp],
     "distegnn_comm_destroy": [_vp],
     "distegnn_allreduce_packed": [_vp, _vp, _i64, _vp],
     "distegnn_loss_packed_floats": [_i32, _i32],

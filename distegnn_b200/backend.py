@@ -234,7 +234,14 @@ class Comm:
         return int(v.value)
 
     def destroy(self) -> None:
+        """Collective teardown: unmap the peers, wait until every rank has done so, then free the own segment."""
         if self.handle is not None:
+            import torch.distributed as dist
+            self.lib.distegnn_comm_disconnect(self.handle)
+            try:
+                dist.barrier(group=self.group)
+            except Exception:        # noqa: BLE001 — process group already gone: nothing left to order against
+                pass
             self.lib.distegnn_comm_destroy(self.handle)
             self.handle = None
 

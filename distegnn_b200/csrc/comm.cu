@@ -130,6 +130,22 @@ extern "C" int distegnn_comm_status(void* comm, int* status_host) {
     return DISTEGNN_OK;
 }
 
+// Unmap the peers' segments (this rank's own segment stays allocated: peers may still have it mapped).  Teardown order
+// across ranks: everybody disconnects -> host barrier -> everybody destroys (CUDA leaves freeing an exported allocation
+// that an importer still maps undefined).
+extern "C" int distegnn_comm_disconnect(void* comm) {
+    if (!comm) return DISTEGNN_OK;
+    CommHost* c = (CommHost*)comm;
+    for (int r = 0; r < c->dev.world; ++r)
+        if (r != c->dev.rank && c->peer_base[r]) {
+            cudaIpcCloseMemHandle(c->peer_base[r]);
+            c->peer_base[r] = nullptr;
+        }
+    (void)cudaGetLastError();
+    c->connected = false;
+    return DISTEGNN_OK;
+}
+
 extern "C" int distegnn_comm_destroy(void* comm) {
     if (!comm) return DISTEGNN_OK;
     CommHost* c = (CommHost*)comm;

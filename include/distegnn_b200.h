@@ -316,7 +316,9 @@ DISTEGNN_API int distegnn_embed_bwd(int64_t n_nodes, int F, int A, int C, int Na
  *   distegnn_comm_connect  all_handles_host = world handles in rank order; maps the peers' segments
  *   distegnn_allreduce_packed  in-place SUM of buf[0:count] over the ranks, enqueued on `stream`
  *   distegnn_comm_status   *status_host != 0 if a wait timed out (a peer never arrived; default 10 s, see _set_timeout_ms)
- *   distegnn_comm_destroy  unmap + free (the caller makes sure no rank still has calls in flight)
+ *   distegnn_comm_disconnect  unmap the peers' segments (own segment stays: peers may still map it)
+ *   distegnn_comm_destroy  unmap + free.  Teardown across ranks: no calls in flight -> every rank disconnects -> host
+ *                          barrier -> every rank destroys (an exported allocation must outlive its importers' mappings)
  * The fused form — all-reduce of vsum[b,:] followed by the virtual-node update in the same kernel — is
  * distegnn_virtual_update_fwd with a non-null `comm`.
  */
@@ -326,6 +328,7 @@ DISTEGNN_API int distegnn_comm_init(int rank, int world, int max_slots, int slot
 DISTEGNN_API int distegnn_comm_connect(void *comm, const void *all_handles_host);
 DISTEGNN_API int distegnn_comm_set_timeout_ms(void *comm, int64_t milliseconds);
 DISTEGNN_API int distegnn_comm_status(void *comm, int *status_host);
+DISTEGNN_API int distegnn_comm_disconnect(void *comm);
 DISTEGNN_API int distegnn_comm_destroy(void *comm);
 DISTEGNN_API int distegnn_allreduce_packed(void *comm, float *buf, int64_t count, void *stream);
 
