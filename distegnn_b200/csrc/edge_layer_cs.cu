@@ -72,6 +72,14 @@ constexpr int CS_THREADS = 1024, CS_GROUPS = 4, CS_GROUP = 256, CS_WARPS = 8;
 // conflicts) keeps every 4-row gather box (4 x 288 B) 128-byte aligned, as TMA tensor copies require
 constexpr int CS_QROW = CS_GATHER4 ? 72 : 68;
 constexpr int CS_QBUF = TILE_M * CS_QROW;
+// Offset (floats) of tile row r in the staging buffer.  With gather4 the buffer is 32 boxes of 4 rows at pitch 72; a pitch of
+// 72 words alone would put rows r and r+4 on the same banks (2-way conflicts for the row-per-thread LDS.128 / STS.128), so
+// the ODD boxes are fetched with a column coordinate of −4: the TMA unit zero-fills the 4 out-of-bounds floats in front and
+// the row data sits 16 bytes further right — 8 consecutive rows then cover all 32 banks exactly once.
+__host__ __device__ constexpr int cs_qoff(int r) {
+    return CS_GATHER4 ? (r >> 2) * (4 * CS_QROW) + (r & 3) * CS_QROW + (((r >> 2) & 1) << 2) : r * CS_QROW;
+}
+static_assert(!CS_GATHER4 || CS_SEGSUM_V2, "the gather4 staging layout is only wired into the straight-pass segment sum");
 constexpr int CS_W = 64 * 64;                             // fp16 elements per weight matrix (8 KB)
 constexpr int CS_IDX = TILE_M * 4;                        // ints per index buffer: row 128 | col 128 | ea 128x2
 constexpr int CS_SMEM_BYTES = 4 * CS_W * 2                // W2 hi/lo, Wc hi/lo
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     const uint32_t tA_hi = lane_off + col0 + 16u * hf, tA_lo = lane_off + col0 + 32u + 16u * hf;   // own 16 words each
     const uint32_t tD = lane_off + col0 + 64u + 32u * hf;                                          // own 32 columns
     float* qb = qbufs + grp * CS_QBUF;
-    float* myq = qb + r * CS_QROW + cb;                          // own half row of the staging buffer
+    float* myq = qb + cs_qoff(r) + cb;                           // own half row of the staging buffer
     int* srow = srow_all + grp * TILE_M;
     uint32_t* rmask = rmask_all + grp * 4;
     int* nidx = nidx_all + grp * 2 * CS_IDX;
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             const int64_t nvalid = min((int64_t)TILE_M, nE - tile * TILE_M);
             mbar_expect_tx(qbar, (uint32_t)nvalid * (H * 4));
         }
-        if (hf == 0 && row_c >= 0) bulk_g2s(qb + r * CS_QROW, a.Q + (size_t)col_c * H, H * 4, qbar);
+        if (hf == 0 && row_c >= 0) bulk_g2s(qb + cs_qoff(r), a.Q + (size_t)col_c * H, H * 4, qbar);
         set_geometry(ldg4(a.x4 + (size_t)max(row_c, 0) * 4), ldg4(a.x4 + (size_t)col_c * 4));
     }
 
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         if (need_m) {
             // warp wk <-> edges 16wk .. 16wk+15 of the tile, lane <-> columns 2·lane, 2·lane+1: per edge one LDS.64
             // and one FADD2; the run structure is warp-uniform, one RED.v2 per run and lane
-            const float* colp = qb + (16 * wk) * CS_QROW + 2 * lane;
+            const float* colp = qb + cs_qoff(16 * wk) + 2 * lane;     // 16·wk is a multiple of 8: row e of the warp sits at cs_qoff(e)
 #if CS_SEGSUM_V2
             // one straight pass over the warp's 16 edges; bit e of M = edge e starts a new run of equal destination rows
             // (warp-uniform), where the running sum is flushed with one RED.v2 per lane
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             f32x2 s0 = *reinterpret_cast<const f32x2*>(colp);
 #pragma unroll
             for (int e = 1; e < 16; ++e) {
-                const f32x2 v = *reinterpret_cast<const f32x2*>(colp + e * CS_QROW);
+                const f32x2 v = *reinterpret_cast<const f32x2*>(colp + cs_qoff(e));
                 if ((M >> e) & 1u) {
                     flush(s0, e - 1);
                     s0 = v;
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int4 c4 = *reinterpret_cast<const int4*>(ncol_s + 16 * wk + 4 * i);
-                    tma_gather4(qb + (16 * wk + 4 * i) * CS_QROW, &tmQ, 0, c4.x, c4.y, c4.z, c4.w, qbar);
+                    tma_gather4(qb + (4 * wk + i) * (4 * CS_QROW), &tmQ, (i & 1) ? -4 : 0, c4.x, c4.y, c4.z, c4.w, qbar);
                 }
             }
             __syncwarp();
