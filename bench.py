@@ -587,9 +587,9 @@ def run_ours(args, w, rank, world, local_rank):
         t_tr = max_over_ranks(s.elapsed_time(e) * 1e-3 / n_tr)
         train = {"value": 1.0 / t_tr, "unit": "train-steps/s", "ms_per_step": t_tr * 1e3, "steps": n_tr,
                  "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
-                 "includes": "forward (sm_100a kernels, activations kept per layer) + backward (hand-written edge and "
-                             "real<->virtual backward kernels, dense per-node stages via torch recompute, packed "
-                             "gradient all-reduce); no optimizer step"}
+                 "includes": "forward (sm_100a kernels, activations kept per layer) + backward (hand-written kernels for every "
+                             "stage: edge and real<->virtual on tcgen05, node stage / embedding / virtual update as fp32 "
+                             "tile kernels; packed gradient exchange); no optimizer step"}
         model.eval()
         for p_ in model.parameters():
             p_.grad = None

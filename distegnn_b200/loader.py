@@ -71,8 +71,10 @@ def collate(shards: Sequence[Shard]) -> Dict[str, Tensor]:
 def batch_to_device(host: Dict[str, Tensor], device, non_blocking: bool = True) -> Tuple[Dict[str, object], Dict[str, object]]:
     """Collated host batch -> (FastEGNN.forward kwargs on `device`, extras)."""
     d = {k: v.to(device, non_blocking=non_blocking) for k, v in host.items() if k != "ptr"}
+    graph = CSRGraph(d["rowptr"], d["col"])
+    graph._checked = True                                    # produced by `collate` from CSR shards: valid by construction
     kwargs = dict(node_feat=d["node_feat"], node_loc=d["node_loc"], node_vel=d["node_vel"], loc_mean=d["loc_mean"],
-                  edge_index=CSRGraph(d["rowptr"], d["col"]), data_batch=d["data_batch"].to(torch.int64),
+                  edge_index=graph, data_batch=d["data_batch"].to(torch.int64),
                   edge_attr=d.get("edge_attr"), node_attr=d.get("node_attr"))
     ptr = host["ptr"].tolist()
     extras = dict(target=d.get("target"), ptr=ptr, n_graphs=len(ptr) - 1,
