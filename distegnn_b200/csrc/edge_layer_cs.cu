@@ -67,7 +67,16 @@ struct EdgeCsArgs {
 #ifndef CS_SEGSUM_V2
 #define CS_SEGSUM_V2 1
 #endif
+//   CS_LDTM_PIPE  1: the accumulator chunks of stages 2 and 3 are read one chunk ahead (tcgen05.ld of chunk j+1 issued
+//                    before the SiLU work on chunk j); 0: load, wait, compute per chunk
+#ifndef CS_LDTM_PIPE
+#define CS_LDTM_PIPE 1
+#endif
+#ifndef CS_S1_UNROLL
+#define CS_S1_UNROLL 2          // chunks (of 8 columns) of stage 1 unrolled together (P / Q loads of both in flight)
+#endif
 constexpr int CS_THREADS = 1024, CS_GROUPS = 4, CS_GROUP = 256, CS_WARPS = 8;
+constexpr int kS1Unroll = CS_S1_UNROLL;
 // padded row pitch of the staging buffer (floats): 68 = conflict-free row-per-thread LDS.128 / STS.128; 72 (2-way
 // conflicts) keeps every 4-row gather box (4 x 288 B) 128-byte aligned, as TMA tensor copies require
 constexpr int CS_QROW = CS_GATHER4 ? 72 : 68;
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         float inv_s1 = 1.0f;
         {
             __half2 mx = __floats2half2_rn(0.f, 0.f);
-#pragma unroll 2
+#pragma unroll kS1Unroll
             for (int j = 0; j < 4; ++j) {
                 f32x2 v[4];
                 uint32_t hi[4], lo[4];
@@ -365,10 +374,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
 
         // ---- stage 2: m = SiLU(D/s + b2), own 32 columns -> shared (segment sum) and fp16 hi/lo -> TMEM ----------
         qmax = 0.f;
-        auto m_chunk = [&](int j, f32x2 (&v)[4], bool store, auto safe) {
-            uint32_t d[8];
-            tmem_ld8(tD + 8 * j, d);
-            wait_ld();
+        auto m_math = [&](int j, const uint32_t (&d)[8], f32x2 (&v)[4], bool store, auto safe) {
             const f32x2 is2 = bc2(inv_s1);
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
@@ -382,9 +388,30 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 v[2 * j4 + 1] = m1;
             }
         };
+        auto m_chunk = [&](int j, f32x2 (&v)[4], bool store, auto safe) {      // cold paths: load, wait, compute
+            uint32_t d[8];
+            tmem_ld8(tD + 8 * j, d);
+            wait_ld();
+            m_math(j, d, v, store, safe);
+        };
         float inv_s2 = 1.0f;
         {
             __half2 mx = __floats2half2_rn(0.f, 0.f);
+#if CS_LDTM_PIPE
+            uint32_t dq[2][8];
+            tmem_ld8(tD, dq[0]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                f32x2 v[4];
+                uint32_t hi[4], lo[4];
+                wait_ld8(dq[j & 1]);
+                if (j < 3) tmem_ld8(tD + 8 * (j + 1), dq[(j + 1) & 1]);
+                m_math(j, dq[j & 1], v, need_m, kFast);
+                split8<false>(v, 1.0f, hi, lo, mx);
+                tmem_st4(tA_hi + 4 * j, hi);
+                tmem_st4(tA_lo + 4 * j, lo);
+            }
+#else
 #pragma unroll 2
             for (int j = 0; j < 4; ++j) {
                 f32x2 v[4];
@@ -394,6 +421,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
+#endif
             const bool bad = __any_sync(FULL, tc16::row_overflow(mx) || silu_q_overflow(qmax));
             if (lane == 0) oflag[CS_WARPS + wk] = bad ? 1u : 0u;
         }
@@ -530,11 +558,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             ph01 = bc2(0.f);
             ph23 = bc2(0.f);
             const f32x2 is2 = bc2(inv_s2);
-#pragma unroll 2
-            for (int j = 0; j < 4; ++j) {
-                uint32_t d[8];
-                tmem_ld8(tD + 8 * j, d);
-                wait_ld();
+            auto phi_math = [&](int j, const uint32_t (&d)[8]) {
 #pragma unroll
                 for (int j4 = 0; j4 < 2; ++j4) {
                     const int cc = cb + 8 * j + 4 * j4;
@@ -546,7 +570,25 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                     ph01 = fma2(s0, ww.x, ph01);
                     ph23 = fma2(s1, ww.y, ph23);
                 }
+            };
+#if CS_LDTM_PIPE
+            uint32_t dq[2][8];
+            tmem_ld8(tD, dq[0]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                wait_ld8(dq[j & 1]);
+                if (j < 3) tmem_ld8(tD + 8 * (j + 1), dq[(j + 1) & 1]);
+                phi_math(j, dq[j & 1]);
             }
+#else
+#pragma unroll 2
+            for (int j = 0; j < 4; ++j) {
+                uint32_t d[8];
+                tmem_ld8(tD + 8 * j, d);
+                wait_ld();
+                phi_math(j, d);
+            }
+#endif
         };
         phi_pass(kFast);
         if (kSiluGuard && __any_sync(FULL, silu_q_overflow(qmax))) phi_pass(kSafe);      // cold (warp-local: no scale)

@@ -19,7 +19,8 @@ namespace tc16 {
 
 constexpr float RANGE = 3.0e4f;
 #ifndef TC16_CHUNK_UNROLL
-#define TC16_CHUNK_UNROLL 2    // chunks (of 16 columns) unrolled in encode_row: code size (I-cache) vs ILP
+#define TC16_CHUNK_UNROLL 1    // chunks (of 16 columns) unrolled in encode_row: code size (I-cache) vs ILP; measured r02 on
+                               // the real<->virtual kernel: 1 -> 1.618 ms, 2 -> 1.676 ms, 4 -> 1.700 ms
 #endif
 constexpr int kChunkUnroll = TC16_CHUNK_UNROLL;
 
@@ -190,6 +191,79 @@ __device__ __forceinline__ float encode_row2_s(F&& f, uint32_t ta_hi, uint32_t t
     }
     return sc;
 }
+// Same contract for stages whose input is a 64-column fp32 accumulator in TMEM at `t_src` (lane offset included): the
+// producer is f(chunk, d[16 raw accumulator words], v[8 pairs], first_pass, flavour tag, qmax).  On the hot pass the
+// accumulator is read one 16-column chunk AHEAD of the SiLU work (tcgen05.ld of chunk c+1 in flight while chunk c is
+// computed): TMEM reads are 64 B/clk/SM and the kernels are latency-bound, so the read must not sit in the dependent chain.
+#ifndef TC16_LDTM_PIPE
+#define TC16_LDTM_PIPE 0          // measured r02 on the thread-per-row real<->virtual kernel (16 warps/SM): no gain (1.667 vs
+#endif                            // 1.665 ms), unlike the 32-warp edge kernel (2.80 -> 2.69 ms, CS_LDTM_PIPE); kept as a knob
+template <class F>
+__device__ __forceinline__ float encode_row2_tm(F&& f, uint32_t t_src, uint32_t ta_hi, uint32_t ta_lo) {
+    __half2 mx = __floats2half2_rn(0.f, 0.f);
+    float qmax = 0.f;
+    {
+#if TC16_LDTM_PIPE
+        uint32_t dq[2][16];
+        umma::tmem_ld16(t_src, dq[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            f32x2 v[8];
+            uint32_t hi[8], lo[8];
+            umma::wait_ld16(dq[c & 1]);
+            if (c < 3) umma::tmem_ld16(t_src + 16 * (c + 1), dq[(c + 1) & 1]);
+            f(c, dq[c & 1], v, true, kFast, qmax);
+            split16p<false>(v, 1.0f, hi, lo, mx);
+            umma::tmem_st8(ta_hi + 8 * c, hi);
+            umma::tmem_st8(ta_lo + 8 * c, lo);
+        }
+#else
+#pragma unroll kChunkUnroll
+        for (int c = 0; c < 4; ++c) {
+            f32x2 v[8];
+            uint32_t hi[8], lo[8], d[16];
+            umma::tmem_ld16(t_src + 16 * c, d);
+            umma::wait_ld();
+            f(c, d, v, true, kFast, qmax);
+            split16p<false>(v, 1.0f, hi, lo, mx);
+            umma::tmem_st8(ta_hi + 8 * c, hi);
+            umma::tmem_st8(ta_lo + 8 * c, lo);
+        }
+#endif
+        if (!__any_sync(FULL, row_overflow(mx) || silu_q_overflow(qmax))) return 1.0f;
+    }
+    float fm = 0.f, sc, inv_unused;                 // cold: per-row range rescue / per-element SiLU flavour
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        f32x2 v[8];
+        uint32_t d[16];
+        umma::tmem_ld16(t_src + 16 * c, d);
+        umma::wait_ld();
+        f(c, d, v, true, kSafe, qmax);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v0, v1;
+            upk2(v[j], v0, v1);
+            fm = fmaxf(fm, fmaxf(fabsf(v0), fabsf(v1)));
+        }
+    }
+    range_scale(fm, sc, inv_unused);
+    sc = fminf(sc, 1.0f);
+    umma::wait_st();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        f32x2 v[8];
+        uint32_t hi[8], lo[8], d[16];
+        umma::tmem_ld16(t_src + 16 * c, d);
+        umma::wait_ld();
+        f(c, d, v, false, kSafe, qmax);
+        split16p<true>(v, sc, hi, lo, mx);
+        umma::tmem_st8(ta_hi + 8 * c, hi);
+        umma::tmem_st8(ta_lo + 8 * c, lo);
+    }
+    return sc == 1.0f ? 1.0f : 1.0f / sc;
+}
+
 template <class F>
 __device__ __forceinline__ float encode_row2(F&& f, uint32_t ta_hi, uint32_t ta_lo) {
     const float sc = encode_row2_s(f, ta_hi, ta_lo, 1.0f);

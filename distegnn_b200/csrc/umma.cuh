@@ -126,6 +126,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
+// tcgen05.wait::ld that also "produces" the 8 registers of an earlier tmem_ld8: consumers of r cannot be scheduled above
+// the wait, which makes it safe to issue the NEXT chunk's load before computing on this one (software pipelining of the
+// TMEM reads: 64 B/clk/SM and ~ a dozen cycles of latency per load).
+__device__ __forceinline__ void wait_ld8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- MMA: D[tmem] (+)= A[tmem] · B[smem]^T, M=128, N=64, K=8 (tf32), issued by ONE thread -------------

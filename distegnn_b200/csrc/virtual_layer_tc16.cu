@@ -226,11 +226,8 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         mma_done();
 
         // ---- stage 2: mv = SiLU(D + b2v) -> shared tile and A ---------------------------------------------
-        const float inv2 = tc16::encode_row2(
-            [&](int c, f32x2 (&v)[8], bool first, auto safe, float& qmax) {
-                uint32_t d[16];
-                tmem_ld16(lane_off + tD + 16 * c, d);
-                wait_ld();
+        const float inv2 = tc16::encode_row2_tm(
+            [&](int c, const uint32_t (&d)[16], f32x2 (&v)[8], bool first, auto safe, float& qmax) {
                 const f32x2 is2 = bc2(inv1);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -244,7 +241,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     v[2 * j4 + 1] = m1;
                 }
             },
-            lane_off + tA_hi, lane_off + tA_lo);
+            lane_off + tD, lane_off + tA_hi, lane_off + tA_lo);
         a_ready();
         issue(dWxvhi, dWxvlo);
         // pools of mv while MMA 2 runs
@@ -296,11 +293,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         auto head_pass = [&](const float* bs, const float* ws, auto safe, float& qmax) {
             f32x2 ph01 = bc2(0.f), ph23 = bc2(0.f);
             const f32x2 is2 = bc2(inv2);
-#pragma unroll tc16::kChunkUnroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t d[16];
-                tmem_ld16(lane_off + tD + 16 * c, d);
-                wait_ld();
+            auto head_math = [&](int c, const uint32_t (&d)[16]) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int cc = 16 * c + 4 * j4;
@@ -312,7 +305,25 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     ph01 = fma2(s0, ww.x, ph01);
                     ph23 = fma2(s1, ww.y, ph23);
                 }
+            };
+#if TC16_LDTM_PIPE
+            uint32_t dq[2][16];                             // accumulator read one chunk ahead of the SiLU work
+            tmem_ld16(lane_off + tD, dq[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                wait_ld16(dq[c & 1]);
+                if (c < 3) tmem_ld16(lane_off + tD + 16 * (c + 1), dq[(c + 1) & 1]);
+                head_math(c, dq[c & 1]);
             }
+#else
+#pragma unroll tc16::kChunkUnroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t d[16];
+                tmem_ld16(lane_off + tD + 16 * c, d);
+                wait_ld();
+                head_math(c, d);
+            }
+#endif
             float p0, p1, p2, p3;
             upk2(ph01, p0, p1);
             upk2(ph23, p2, p3);
