@@ -72,6 +72,9 @@ struct EdgeCsArgs {
 #ifndef CS_LDTM_PIPE
 #define CS_LDTM_PIPE 1
 #endif
+#ifndef CS_REFILL_BARRIER
+#define CS_REFILL_BARRIER 0     // 1: group barrier before the staging buffer is refilled (r01); 0: per-warp ordering only
+#endif
 #ifndef CS_S1_UNROLL
 #define CS_S1_UNROLL 2          // chunks (of 8 columns) of stage 1 unrolled together (P / Q loads of both in flight)
 #endif
@@ -94,7 +97,7 @@ constexpr int CS_IDX = TILE_M * 4;                        // ints per index buff
 constexpr int CS_SMEM_BYTES = 4 * CS_W * 2                // W2 hi/lo, Wc hi/lo
                               + CS_GROUPS * CS_QBUF * 4
                               + (4 * H + DISTEGNN_MAX_EDGE_ATTR * H) * 4   // b2, bc, w3, w1r, w1e
-                              + CS_GROUPS * TILE_M * 4        // srow
+                              + CS_GROUPS * 2 * TILE_M * 4    // srow, double buffered by tile parity
                               + CS_GROUPS * 4 * 4             // run-start bit masks (one word per lane quarter)
                               + CS_GROUPS * 2 * CS_IDX * 4    // staged indices of the next tile, double buffered
                               + CS_GROUPS * 2 * CS_WARPS * 4  // out-of-range flags per warp, one set per stage
@@ -148,8 +151,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     float* w3s = bcs + H;
     float* w1rs = w3s + H;
     float* w1es = w1rs + H;
-    int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);      // [4][128]
-    uint32_t* rmask_all = reinterpret_cast<uint32_t*>(srow_all + CS_GROUPS * TILE_M);   // [4][4]
+    int* srow_all = reinterpret_cast<int*>(w1es + DISTEGNN_MAX_EDGE_ATTR * H);      // [4][2][128]
+    uint32_t* rmask_all = reinterpret_cast<uint32_t*>(srow_all + CS_GROUPS * 2 * TILE_M);   // [4][4]
     int* nidx_all = reinterpret_cast<int*>(rmask_all + CS_GROUPS * 4);              // [4][2][CS_IDX]
     uint32_t* oflag_all = reinterpret_cast<uint32_t*>(nidx_all + CS_GROUPS * 2 * CS_IDX);   // [4][2][8]
     float* rowmax_all = reinterpret_cast<float*>(oflag_all + CS_GROUPS * 2 * CS_WARPS);      // [4][2][128]
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     const uint32_t tD = lane_off + col0 + 64u + 32u * hf;                                          // own 32 columns
     float* qb = qbufs + grp * CS_QBUF;
     float* myq = qb + cs_qoff(r) + cb;                           // own half row of the staging buffer
-    int* srow = srow_all + grp * TILE_M;
+    int* srow2 = srow_all + grp * 2 * TILE_M;
     uint32_t* rmask = rmask_all + grp * 4;
     int* nidx = nidx_all + grp * 2 * CS_IDX;
     uint32_t* oflag = oflag_all + grp * 2 * CS_WARPS;
@@ -281,6 +284,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         const int* ncol_s = nrow_s + TILE_M;
         const float* nea_s = reinterpret_cast<const float*>(ncol_s + TILE_M);
         const bool nvalid_r = ntile < num_tiles && ntile * TILE_M + r < nE;     // edge r of the next tile exists
+        // destination rows of this tile's edges, per tile parity: a fast warp writes the NEXT tile's rows (stage 1) while a slow
+        // one may still read this tile's in the segment sum — no group barrier separates the two any more
+        int* srow = srow2 + (it & 1) * TILE_M;
 
         // ---- stage 1: a1 = SiLU(P_i + Q_j + w_r·r + W_e·a), own 32 columns -> fp16 hi/lo -> TMEM ---------------
         mbar_wait(qbar, (uint32_t)(it & 1));
@@ -509,8 +515,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             }
 #endif
         }
-        fence_proxy_async_smem();              // generic accesses to qb ordered before the TMA refill below
-        named_bar(bar_id, CS_GROUP);           // whole group done with the staging buffer
+        // The rows a warp refills (16·wk .. +15) were last read by that same warp (segment sum) — their stage-1 / stage-2
+        // accesses by the owner threads lie before the previous group barrier — so no group barrier is needed here: warp-level
+        // ordering of the generic accesses before the async-proxy refill is enough (r02: this barrier was 6 % of the samples).
+        fence_proxy_async_smem();
+#if CS_REFILL_BARRIER
+        named_bar(bar_id, CS_GROUP);
+#else
+        __syncwarp();
+#endif
 
         // ---- Q rows of the next tile, addresses from the staged indices ----------------------------------------------------
         if (ntile < num_tiles) {
