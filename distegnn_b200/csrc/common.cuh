@@ -166,6 +166,34 @@ __device__ __forceinline__ void silu4p(f32x2& a, f32x2& b, float& qmax) {
     b = mul2(b, mul2(u, da));                                 // x · (1/d2, 1/d3)
 #endif
 }
+// The same in the "t domain": the inputs are t = −log2(e)·x (the producer folds the factor into its weights / biases), the
+// outputs s = t / (1 + 2^t) = −log2(e)·SiLU(x) — the consumer folds −ln 2 into whatever multiplies s next.  Saves the
+// FMUL2 per pair that forms the exponent argument.
+constexpr float SILU_T_IN = -1.4426950408889634f;    // t = SILU_T_IN · x
+constexpr float SILU_T_OUT = -0.6931471805599453f;   // SiLU(x) = SILU_T_OUT · s
+__device__ __forceinline__ f32x2 silu_den2_t(f32x2 t) {
+    float t0, t1;
+    upk2(t, t0, t1);
+    return add2(pk2(ex2_approx(t0), ex2_approx(t1)), bc2(1.0f));
+}
+template <bool SAFE>
+__device__ __forceinline__ void silu4t(f32x2& a, f32x2& b, float& qmax) {
+    const f32x2 da = silu_den2_t(a), db = silu_den2_t(b);
+    if (SAFE || !kSiluGuard) {
+        a = mul2(a, rcp2(da));
+        b = mul2(b, rcp2(db));
+        return;
+    }
+    const f32x2 p = mul2(da, db);
+    float p0, p1;
+    upk2(p, p0, p1);
+    const float q = p0 * p1;
+    qmax = fmaxf(qmax, q);
+    const float r = rcp_approx(q);
+    const f32x2 u = pk2(r * p1, r * p0);
+    a = mul2(a, mul2(u, db));
+    b = mul2(b, mul2(u, da));
+}
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }

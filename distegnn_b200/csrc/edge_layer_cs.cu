@@ -78,6 +78,26 @@ struct EdgeCsArgs {
 #ifndef CS_S1_UNROLL
 #define CS_S1_UNROLL 2          // chunks (of 8 columns) of stage 1 unrolled together (P / Q loads of both in flight)
 #endif
+#ifndef CS_X_STAGED
+#define CS_X_STAGED 1           // 1: the next tile's coordinates x[row], x[col] are gathered by cp.async into shared memory (one
+#endif                          // copy per edge, issued after the stage-1 barrier, visible to both column halves after the
+                                // stage-2 barrier); 0: every thread loads them with LDG after the segment sum (r02 ncu: the
+                                // outstanding random gather shares a scoreboard with later instructions and stalls the warp for
+                                // 5 % of the kernel right after the MMA-2 wait)
+#ifndef CS_P_AHEAD
+#define CS_P_AHEAD 1            // 1: stage 1 requests P[row] one chunk ahead (chunk 0 at the end of the previous tile)
+#endif
+#ifndef CS_SCHED_FENCE
+#define CS_SCHED_FENCE 0        // bit mask of the stages (1, 2, 4 = stage 1, 2, 3) whose read-ahead load is pinned above the
+#endif                          // current chunk's math by a scheduling fence (__syncwarp: no instruction, but ptxas does not
+                                // move code across it).  Without it ptxas sinks the read-ahead tcgen05.ld of stages 2 / 3 below
+                                // the math; measured r02: all three pinned 2.611 ms, none pinned 2.594 ms -> default 0
+#ifndef CS_TDOMAIN
+#define CS_TDOMAIN 1            // 1: stages 2 and 3 run in the "t domain" (common.cuh silu4t): W2 and the biases b2 / bc carry
+#endif                          // −log2(e), w3 and the segment-sum flush carry −ln 2, and the per-pair FMUL2 that forms the
+                                // exponent argument disappears from both stages; 0: plain SiLU on x
+constexpr bool kNeg2 = CS_TDOMAIN;      // stage-2 values are ≤ 0.41 and unbounded below in the t domain
+constexpr float kTIn = CS_TDOMAIN ? SILU_T_IN : 1.0f, kTOut = CS_TDOMAIN ? SILU_T_OUT : 1.0f;
 constexpr int CS_THREADS = 1024, CS_GROUPS = 4, CS_GROUP = 256, CS_WARPS = 8;
 constexpr int kS1Unroll = CS_S1_UNROLL;
 // padded row pitch of the staging buffer (floats): 68 = conflict-free row-per-thread LDS.128 / STS.128; 72 (2-way
@@ -91,6 +111,7 @@ constexpr int CS_QBUF = TILE_M * CS_QROW;
 __host__ __device__ constexpr int cs_qoff(int r) {
     return CS_GATHER4 ? (r >> 2) * (4 * CS_QROW) + (r & 3) * CS_QROW + (((r >> 2) & 1) << 2) : r * CS_QROW;
 }
+static_assert(!CS_TDOMAIN || CS_SEGSUM_V2, "the t-domain flush factor is only wired into the straight-pass segment sum");
 static_assert(!CS_GATHER4 || CS_SEGSUM_V2, "the gather4 staging layout is only wired into the straight-pass segment sum");
 constexpr int CS_W = 64 * 64;                             // fp16 elements per weight matrix (8 KB)
 constexpr int CS_IDX = TILE_M * 4;                        // ints per index buffer: row 128 | col 128 | ea 128x2
@@ -102,39 +123,40 @@ constexpr int CS_SMEM_BYTES = 4 * CS_W * 2                // W2 hi/lo, Wc hi/lo
                               + CS_GROUPS * 2 * CS_IDX * 4    // staged indices of the next tile, double buffered
                               + CS_GROUPS * 2 * CS_WARPS * 4  // out-of-range flags per warp, one set per stage
                               + CS_GROUPS * 2 * TILE_M * 4    // row maxima of the two column halves (cold path)
+                              + (CS_X_STAGED ? CS_GROUPS * TILE_M * 8 * 4 : 0)   // x[row], x[col] of the next tile's edges
                               + 128;                          // mbarriers + tmem base
 constexpr uint32_t CS_LBO = 1024;                         // fp16 K-major no-swizzle, N = 64
 using tc16::kFast;
 using tc16::kSafe;
 
-// 8 fp32 values held as 4 register pairs (·s) -> 4 packed hi words + 4 packed lo words
-template <bool SCALED>
+// 8 fp32 values held as 4 register pairs (·s) -> 4 packed hi words + 4 packed lo words.  `mx` tracks the side of the values
+// that can leave the fp16 range: SiLU outputs are bounded below (−0.28), so the positive side — or, for t-domain values
+// (NEG: s = −log2(e)·SiLU), the negative one, tracked as a running minimum.
+template <bool SCALED, bool NEG>
 __device__ __forceinline__ void split8(const f32x2 (&v)[4], float s, uint32_t (&hi)[4], uint32_t (&lo)[4], __half2& mx) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const f32x2 x = SCALED ? mul2(v[j], bc2(s)) : v[j];
-        float x0, x1, l0, l1;
-        upk2(x, x0, x1);
-        const __half2 h = __floats2half2_rn(x0, x1);            // x0 -> low half (even k)
-        const float2 hf = __half22float2(h);
-        upk2(sub2(x, pk2(hf.x, hf.y)), l0, l1);
-        const __half2 l = __floats2half2_rn(l0, l1);
-        mx = __hmax2(mx, h);                                    // SiLU outputs: only the positive side can overflow
-        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+        tc16::split_pair(SCALED ? mul2(v[j], bc2(s)) : v[j], hi[j], lo[j]);
+        const __half2 h = *reinterpret_cast<const __half2*>(&hi[j]);
+        mx = NEG ? __hmin2(mx, h) : __hmax2(mx, h);
     }
 }
+template <bool NEG>
+__device__ __forceinline__ bool row_overflow8(__half2 mx) {
+    return NEG ? fminf(__low2float(mx), __high2float(mx)) < -tc16::RANGE : tc16::row_overflow(mx);
+}
+template <bool NEG>
 __device__ __forceinline__ float max8(const f32x2 (&v)[4], float fm) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float v0, v1;
         upk2(v[j], v0, v1);
-        fm = fmaxf(fm, fmaxf(v0, v1));
+        fm = NEG ? fmaxf(fm, -fminf(v0, v1)) : fmaxf(fm, fmaxf(v0, v1));
     }
     return fm;
 }
 
-template <int AT>
+template <int AT, bool LASTL>
 __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const EdgeCsArgs a,
                                                                       const __grid_constant__ CUtensorMap tmQ) {
     using namespace umma;
@@ -156,7 +178,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     int* nidx_all = reinterpret_cast<int*>(rmask_all + CS_GROUPS * 4);              // [4][2][CS_IDX]
     uint32_t* oflag_all = reinterpret_cast<uint32_t*>(nidx_all + CS_GROUPS * 2 * CS_IDX);   // [4][2][8]
     float* rowmax_all = reinterpret_cast<float*>(oflag_all + CS_GROUPS * 2 * CS_WARPS);      // [4][2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rowmax_all + CS_GROUPS * 2 * TILE_M);       // [4][2]
+    float* xs_all = rowmax_all + CS_GROUPS * 2 * TILE_M;                                       // [4][128][8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs_all + (CS_X_STAGED ? CS_GROUPS * TILE_M * 8 : 0));   // [4][2]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * CS_GROUPS);
 
     const int tid = threadIdx.x;
@@ -170,15 +193,20 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     const int cb = 32 * hf;                // first owned column
     const int A = AT >= 0 ? AT : a.A;
     const bool normalize = a.flags & DISTEGNN_FLAG_NORMALIZE;
-    const bool need_m = !(a.flags & DISTEGNN_FLAG_LAST);
+    // ptxas schedules freely inside a basic block and may sink a read-ahead load below the math of the current chunk;
+    // sched_fence(stage bit) pins it (A/B knob CS_SCHED_FENCE).
+    auto sched_fence = [&](int stage_bit) {
+        if (CS_SCHED_FENCE & stage_bit) __syncwarp();
+    };
+    constexpr bool need_m = !LASTL;        // the last layer only moves coordinates (DISTEGNN_FLAG_LAST): no segment sum of m
 
     // ---- one-time setup -------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, CS_THREADS);
-    tc16::stage_weight(Wchi, Wclo, a.wc, 0, 64, tid, CS_THREADS);
+    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, CS_THREADS, kTIn);     // t2 = kTIn·(a1·W2ᵀ + b2)
+    tc16::stage_weight(Wchi, Wclo, a.wc, 0, 64, tid, CS_THREADS);           // t3 = s2·Wcᵀ + kTIn·bc  (kTIn·kTOut = 1)
     if (tid < H) {
-        b2s[tid] = a.b2[tid];
-        bcs[tid] = a.bc[tid];
-        w3s[tid] = a.w3[tid];
+        b2s[tid] = a.b2[tid] * kTIn;
+        bcs[tid] = a.bc[tid] * kTIn;
+        w3s[tid] = a.w3[tid] * kTOut;
         w1rs[tid] = a.w1r[tid];
     }
     for (int i = tid; i < DISTEGNN_MAX_EDGE_ATTR * H; i += CS_THREADS) w1es[i] = i < A * H ? a.w1e[i] : 0.f;
@@ -205,6 +233,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     int* nidx = nidx_all + grp * 2 * CS_IDX;
     uint32_t* oflag = oflag_all + grp * 2 * CS_WARPS;
     float* rowmax = rowmax_all + grp * 2 * TILE_M;
+    float* xs = xs_all + grp * TILE_M * 8 + 8 * r;               // (x_row, x_col) of edge r of the next tile
     uint64_t* qbar = bars + grp * 2;
     uint64_t* mbar = bars + grp * 2 + 1;
     const uint32_t bar_id = 1 + grp;
@@ -244,6 +273,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         cp_async_commit();
     };
 
+    ulonglong2 p_first[2];        // CS_P_AHEAD: the first 8 own columns of P[row] of the tile about to be processed
+    p_first[0] = p_first[1] = make_ulonglong2(0ull, 0ull);
     int row_c = -1;
     float dx = 0.f, dy = 0.f, dz = 0.f, radial = 0.f;
     float ea_c[AMAX];
@@ -275,6 +306,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         }
         if (hf == 0 && row_c >= 0) bulk_g2s(qb + cs_qoff(r), a.Q + (size_t)col_c * H, H * 4, qbar);
         set_geometry(ldg4(a.x4 + (size_t)max(row_c, 0) * 4), ldg4(a.x4 + (size_t)col_c * 4));
+#if CS_P_AHEAD
+        p_first[0] = __ldg(reinterpret_cast<const ulonglong2*>(a.P + (size_t)max(row_c, 0) * H + cb));
+        p_first[1] = __ldg(reinterpret_cast<const ulonglong2*>(a.P + (size_t)max(row_c, 0) * H + cb + 4));
+#endif
     }
 
     for (int it = 0; tile < num_tiles; ++it, tile += stride) {
@@ -295,14 +330,14 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         const float* prow = a.P + (size_t)max(row_c, 0) * H + cb;
         float qmax = 0.f;
         const f32x2 rad2 = bc2(radial);
-        auto pre_chunk = [&](int j, f32x2 (&v)[4], auto safe) {
+        // P values of chunk j (8 columns) arrive as `pp`: on the hot path they were requested one chunk earlier (CS_P_AHEAD)
+        auto pre_math = [&](int j, const ulonglong2 (&pp)[2], f32x2 (&v)[4], auto safe) {
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
                 const int cc = 8 * j + 4 * j4;               // relative to the own half
-                const ulonglong2 pp = __ldg(reinterpret_cast<const ulonglong2*>(prow + cc));
                 const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(myq + cc);
                 const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(w1rs + cb + cc);
-                f32x2 p0 = fma2(rad2, wr.x, add2(pp.x, qq.x)), p1 = fma2(rad2, wr.y, add2(pp.y, qq.y));
+                f32x2 p0 = fma2(rad2, wr.x, add2(pp[j4].x, qq.x)), p1 = fma2(rad2, wr.y, add2(pp[j4].y, qq.y));
 #pragma unroll
                 for (int k = 0; k < AMAX; ++k)
                     if (AT < 0 || k < A) {     // AT < 0: ea_c[k] = 0 and zero weight rows beyond A (a predicated FFMA2
@@ -317,19 +352,47 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 v[2 * j4 + 1] = p1;
             }
         };
+        auto load_p = [&](const float* base, int j, ulonglong2 (&pp)[2]) {
+            pp[0] = __ldg(reinterpret_cast<const ulonglong2*>(base + 8 * j));
+            pp[1] = __ldg(reinterpret_cast<const ulonglong2*>(base + 8 * j + 4));
+        };
+        auto pre_chunk = [&](int j, f32x2 (&v)[4], auto safe) {      // cold paths: load, then compute
+            ulonglong2 pp[2];
+            load_p(prow, j, pp);
+            pre_math(j, pp, v, safe);
+        };
         float inv_s1 = 1.0f;
         {
             __half2 mx = __floats2half2_rn(0.f, 0.f);
+#if CS_P_AHEAD
+            // P[row] comes from L2 (the rows of a tile are few, but L1 keeps little between tiles): chunk 0 was requested at
+            // the end of the previous tile (p_first), chunk j+1 is requested before the math of chunk j
+            ulonglong2 pq[2][2];
+            pq[0][0] = p_first[0];
+            pq[0][1] = p_first[1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                f32x2 v[4];
+                uint32_t hi[4], lo[4];
+                if (j < 3) load_p(prow, j + 1, pq[(j + 1) & 1]);
+                sched_fence(1);
+                pre_math(j, pq[j & 1], v, kFast);
+                split8<false, false>(v, 1.0f, hi, lo, mx);
+                tmem_st4(tA_hi + 4 * j, hi);
+                tmem_st4(tA_lo + 4 * j, lo);
+            }
+#else
 #pragma unroll kS1Unroll
             for (int j = 0; j < 4; ++j) {
                 f32x2 v[4];
                 uint32_t hi[4], lo[4];
                 pre_chunk(j, v, kFast);
-                split8<false>(v, 1.0f, hi, lo, mx);
+                split8<false, false>(v, 1.0f, hi, lo, mx);
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
-            const bool bad = __any_sync(FULL, tc16::row_overflow(mx) || silu_q_overflow(qmax));
+#endif
+            const bool bad = __any_sync(FULL, row_overflow8<false>(mx) || silu_q_overflow(qmax));
             if (lane == 0) oflag[wk] = bad ? 1u : 0u;
         }
         wait_st();
@@ -345,7 +408,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             for (int j = 0; j < 4; ++j) {
                 f32x2 v[4];
                 pre_chunk(j, v, kSafe);
-                fm = max8(v, fm);
+                fm = max8<false>(v, fm);
             }
             rowmax[hf * TILE_M + r] = fm;
             named_bar(bar_id, CS_GROUP);
@@ -356,7 +419,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 f32x2 v[4];
                 uint32_t hi[4], lo[4];
                 pre_chunk(j, v, kSafe);
-                split8<true>(v, sc, hi, lo, mx);
+                split8<true, false>(v, sc, hi, lo, mx);
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
@@ -371,6 +434,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             const int prev = r > 0 ? srow[r - 1] : -2;
             const uint32_t starts = __ballot_sync(FULL, prev != row_c);
             if (lane == 0) rmask[wq] = starts;
+#if CS_X_STAGED
+            if (nvalid_r) {        // coordinates of the next tile's edge: one gather per edge, consumed after stage 3
+                cp_async16(xs, a.x4 + (size_t)nrow_s[r] * 4);
+                cp_async16(xs + 4, a.x4 + (size_t)ncol_s[r] * 4);
+            }
+            cp_async_commit();
+#endif
         }
         if (nvalid_r) prefetch_l1(a.P + (size_t)nrow_s[r] * H + cb);      // one 128-byte line per thread
 
@@ -388,7 +458,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(b2s + cb + cc);
                 f32x2 m0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
                 f32x2 m1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+#if CS_TDOMAIN
+                silu4t<decltype(safe)::value>(m0, m1, qmax);     // (m0, m1) = kTIn·m: the flush and Wc's consumer undo it
+#else
                 silu4p<decltype(safe)::value>(m0, m1, qmax);
+#endif
                 if (store) *reinterpret_cast<ulonglong2*>(myq + cc) = make_ulonglong2(m0, m1);
                 v[2 * j4] = m0;
                 v[2 * j4 + 1] = m1;
@@ -412,8 +486,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 uint32_t hi[4], lo[4];
                 wait_ld8(dq[j & 1]);
                 if (j < 3) tmem_ld8(tD + 8 * (j + 1), dq[(j + 1) & 1]);
+                sched_fence(2);
                 m_math(j, dq[j & 1], v, need_m, kFast);
-                split8<false>(v, 1.0f, hi, lo, mx);
+                split8<false, kNeg2>(v, 1.0f, hi, lo, mx);
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
@@ -423,15 +498,18 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 f32x2 v[4];
                 uint32_t hi[4], lo[4];
                 m_chunk(j, v, need_m, kFast);
-                split8<false>(v, 1.0f, hi, lo, mx);
+                split8<false, kNeg2>(v, 1.0f, hi, lo, mx);
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
 #endif
-            const bool bad = __any_sync(FULL, tc16::row_overflow(mx) || silu_q_overflow(qmax));
+            const bool bad = __any_sync(FULL, row_overflow8<kNeg2>(mx) || silu_q_overflow(qmax));
             if (lane == 0) oflag[CS_WARPS + wk] = bad ? 1u : 0u;
         }
         wait_st();
+#if CS_X_STAGED
+        if (hf == 0) cp_async_wait_all();      // the staged coordinates: visible to both halves after the barrier
+#endif
         fence_before_sync();
         named_bar(bar_id, CS_GROUP);           // m tile visible in shared, A complete, D fully read
         if (group_flag(1)) {                   // cold
@@ -440,7 +518,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             for (int j = 0; j < 4; ++j) {
                 f32x2 v[4];
                 m_chunk(j, v, need_m, kSafe);  // also rewrites the m row in shared memory
-                fm = max8(v, fm);
+                fm = max8<kNeg2>(v, fm);
             }
             rowmax[hf * TILE_M + r] = fm;
             named_bar(bar_id, CS_GROUP);
@@ -451,7 +529,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 f32x2 v[4];
                 uint32_t hi[4], lo[4];
                 m_chunk(j, v, false, kSafe);
-                split8<true>(v, sc, hi, lo, mx);
+                split8<true, kNeg2>(v, sc, hi, lo, mx);
                 tmem_st4(tA_hi + 4 * j, hi);
                 tmem_st4(tA_lo + 4 * j, lo);
             }
@@ -475,7 +553,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 const int rr = srw[e_last];
                 if (rr >= 0) {
                     float v0, v1;
-                    upk2(acc, v0, v1);
+                    upk2(CS_TDOMAIN ? mul2(acc, bc2(kTOut)) : acc, v0, v1);
                     red_add_v2(a.agg_m + (size_t)rr * H + 2 * lane, v0, v1);
                 }
             };
@@ -556,8 +634,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         float4 xi_n = make_float4(0.f, 0.f, 0.f, 0.f), xj_n = xi_n;
         if (nvalid_r) {
             row_n = nrow_s[r];
+#if !CS_X_STAGED
             xi_n = ldg4(a.x4 + (size_t)row_n * 4);
             xj_n = ldg4(a.x4 + (size_t)ncol_s[r] * 4);
+#endif
         }
 
         mbar_wait(mbar, 1);
@@ -579,7 +659,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                     const ulonglong2 ww = *reinterpret_cast<const ulonglong2*>(w3s + cc);
                     f32x2 s0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
                     f32x2 s1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+#if CS_TDOMAIN
+                    silu4t<decltype(safe)::value>(s0, s1, qmax);
+#else
                     silu4p<decltype(safe)::value>(s0, s1, qmax);
+#endif
                     ph01 = fma2(s0, ww.x, ph01);
                     ph23 = fma2(s1, ww.y, ph23);
                 }
@@ -591,6 +675,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             for (int j = 0; j < 4; ++j) {
                 wait_ld8(dq[j & 1]);
                 if (j < 3) tmem_ld8(tD + 8 * (j + 1), dq[(j + 1) & 1]);
+                sched_fence(4);
                 phi_math(j, dq[j & 1]);
             }
 #else
@@ -610,6 +695,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         upk2(ph23, ph2, ph3);
         const float phi = (ph0 + ph1) + (ph2 + ph3);
         fence_before_sync();                   // D reads ordered before the next tile's MMA 1
+#if CS_P_AHEAD
+        {   // the next tile's first P chunk: in flight across the shuffle reduction, the roll and the wait for the Q rows
+            const float* pn = a.P + (size_t)max(row_n, 0) * H + cb;
+            p_first[0] = __ldg(reinterpret_cast<const ulonglong2*>(pn));
+            p_first[1] = __ldg(reinterpret_cast<const ulonglong2*>(pn + 4));
+        }
+#endif
         {
             float sx = dx * phi, sy = dy * phi, sz = dz * phi;
 #pragma unroll
@@ -646,6 +738,12 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                     if (k < A) ea_c[k] = __ldg(a.ea + e * A + k);
             }
         }
+#if CS_X_STAGED
+        if (nvalid_r) {
+            xi_n = *reinterpret_cast<const float4*>(xs);
+            xj_n = *reinterpret_cast<const float4*>(xs + 4);
+        }
+#endif
         set_geometry(xi_n, xj_n);
     }
 
@@ -670,7 +768,7 @@ extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, 
     DEGNN_CHECK_ARG((flags & DISTEGNN_FLAG_LAST) || agg_m, "null agg_m");
     Layout L = make_layout(A, C, Na);
     EdgeCsArgs a;
-    a.N = n_nodes; a.E = n_edges; a.E_dev = n_edges_dev; a.A = A; a.flags = flags;
+    a.N = n_nodes; a.E = n_edges; a.E_dev = n_edges_dev; a.A = A; a.flags = flags & 0xffffu;
     a.row = row; a.col = col; a.ea = edge_attr_sorted; a.x4 = x4; a.P = P; a.Q = Q;
     a.w1r = layer_params + L.off[DISTEGNN_P_E_W1R];
     a.w1e = layer_params + L.off[DISTEGNN_P_E_W1E];
@@ -693,11 +791,12 @@ extern "C" int distegnn_edge_layer_fwd(int64_t n_nodes, int64_t n_edges, int A, 
         ensure_dynamic_smem((const void*)kern, (int)CS_SMEM_BYTES);
         kern<<<(unsigned)grid, CS_THREADS, CS_SMEM_BYTES, (cudaStream_t)stream>>>(a, tmQ);
     };
+    const bool last = flags & DISTEGNN_FLAG_LAST;
     switch (A) {
-        case 0: launch(edge_layer_cs_kernel<0>); break;
-        case 1: launch(edge_layer_cs_kernel<1>); break;
-        case 2: launch(edge_layer_cs_kernel<2>); break;
-        default: launch(edge_layer_cs_kernel<-1>); break;
+        case 0: last ? launch(edge_layer_cs_kernel<0, true>) : launch(edge_layer_cs_kernel<0, false>); break;
+        case 1: last ? launch(edge_layer_cs_kernel<1, true>) : launch(edge_layer_cs_kernel<1, false>); break;
+        case 2: last ? launch(edge_layer_cs_kernel<2, true>) : launch(edge_layer_cs_kernel<2, false>); break;
+        default: last ? launch(edge_layer_cs_kernel<-1, true>) : launch(edge_layer_cs_kernel<-1, false>); break;
     }
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;

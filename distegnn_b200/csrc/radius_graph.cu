@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) radius_kernel(const RadiusArgs a) {
                 const float4 pj = ldg4(a.x4 + (size_t)j * 4);
                 const float ddx = p.x - pj.x, ddy = p.y - pj.y, ddz = p.z - pj.z;
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                if (d2 <= a.r2) {
+                if (d2 < a.r2) {          // strict, as torch_cluster
                     if (FILL) {
                         a.row[w] = i;
                         a.col[w] = j;

@@ -23,14 +23,36 @@ constexpr float RANGE = 3.0e4f;
                                // the real<->virtual kernel: 1 -> 1.618 ms, 2 -> 1.676 ms, 4 -> 1.700 ms
 #endif
 constexpr int kChunkUnroll = TC16_CHUNK_UNROLL;
+#ifndef TC16_FHFMA_SPLIT
+#define TC16_FHFMA_SPLIT 1     // 1: lo = x − hi as ONE mixed-precision FMA per element (fma.rn.f32.f16, SASS FHFMA with a
+#endif                         // half selector on the packed hi word); 0: unpack hi to fp32 (2 HADD2.F32) + FADD2
+
+// (hi, lo) fp16 pairs of the fp32 pair x: hi = rn(x), lo = rn(x − hi).  x − hi is exact in fp32 (hi is within half an fp16
+// ulp of x), so both flavours give the same bits.
+__device__ __forceinline__ void split_pair(f32x2 x, uint32_t& hi, uint32_t& lo) {
+    float x0, x1, l0, l1;
+    upk2(x, x0, x1);
+    const __half2 h = __floats2half2_rn(x0, x1);                // x0 -> low half (even k)
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+#if TC16_FHFMA_SPLIT
+    asm("{\n\t.reg .b16 h0, h1, m1;\n\tmov.b32 {h0, h1}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, h0, m1, %3;\n\tfma.rn.f32.f16 %1, h1, m1, %4;\n\t}"
+        : "=f"(l0), "=f"(l1) : "r"(hi), "f"(x0), "f"(x1));
+#else
+    const float2 hf = __half22float2(h);
+    upk2(sub2(x, pk2(hf.x, hf.y)), l0, l1);
+#endif
+    const __half2 l = __floats2half2_rn(l0, l1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // stage W[n][k] (given k-major: wt[k*64+n]) as rows n_off..n_off+63 of an N_total-row B operand, fp16 hi/lo
 __device__ __forceinline__ void stage_weight(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int n_off,
-                                             int n_total, int tid, int nthreads) {
+                                             int n_total, int tid, int nthreads, float scale = 1.0f) {
     const uint32_t lbo_h = (uint32_t)(n_total / 8) * 64u;     // halfs per K chunk of 8
     for (int i = tid; i < H * H; i += nthreads) {
         const int k = i >> 6, n = (i & 63) + n_off;
-        const float w = __ldg(wt_kmajor + i);
+        const float w = __ldg(wt_kmajor + i) * scale;
         const __half h = __float2half_rn(w);
         const uint32_t o = (uint32_t)(k >> 3) * lbo_h + (uint32_t)(n >> 3) * 64u + (uint32_t)(n & 7) * 8u + (k & 7);
         hi[o] = h;
@@ -131,16 +153,8 @@ __device__ __forceinline__ void split16p(const f32x2 (&v)[8], float s, uint32_t 
                                          __half2& mx) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const f32x2 x = SCALED ? mul2(v[j], bc2(s)) : v[j];
-        float x0, x1, l0, l1;
-        upk2(x, x0, x1);
-        const __half2 h = __floats2half2_rn(x0, x1);            // x0 -> low half (even k)
-        const float2 hf = __half22float2(h);
-        upk2(sub2(x, pk2(hf.x, hf.y)), l0, l1);
-        const __half2 l = __floats2half2_rn(l0, l1);
-        mx = __hmax2(mx, __habs2(h));
-        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+        split_pair(SCALED ? mul2(v[j], bc2(s)) : v[j], hi[j], lo[j]);
+        mx = __hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&hi[j])));
     }
 }
 // Same contract as encode_row_s, for producers f(chunk, v[8 pairs], first_pass, flavour tag, qmax) that run their
@@ -212,6 +226,7 @@ __device__ __forceinline__ float encode_row2_tm(F&& f, uint32_t t_src, uint32_t 
             uint32_t hi[8], lo[8];
             umma::wait_ld16(dq[c & 1]);
             if (c < 3) umma::tmem_ld16(t_src + 16 * (c + 1), dq[(c + 1) & 1]);
+            __syncwarp();      // scheduling fence: without it ptxas sinks the read-ahead load below this chunk's math
             f(c, dq[c & 1], v, true, kFast, qmax);
             split16p<false>(v, 1.0f, hi, lo, mx);
             umma::tmem_st8(ta_hi + 8 * c, hi);

@@ -10,6 +10,8 @@
 // All three 64x64 layers run as kind::f16 tile GEMMs with the fp16 2-term split (tc16.cuh); TMEM per group:
 // A_hi 32 + A_lo 32 + D 64 columns (the two coordinate heads reuse D one after the other).
 //   stage 1  a1 = SiLU(Hn[node] + G[graph,c] + w_r·‖ΔX‖)  -> A              MMA 1: D = a1·W2vᵀ
+//            (the tile's Hn rows — one contiguous block — arrive by ONE TMA bulk copy issued a tile ahead into the mv
+//             tile's shared memory, which is idle between the pools of mv and the next tile's stage 2: V16_HN_TMA)
 //   stage 2  mv = SiLU(D + b2v) -> shared tile + A                            MMA 2: D = mv·Wxvᵀ
 //            (while it runs: agg_v[node] = mean_c mv, per-graph Σ_i mv accumulated in shared memory)
 //   stage 3a φ_xv = w3xv·SiLU(D + bxv)                                        MMA 3: D = mv·WXᵀ
@@ -36,8 +38,17 @@ struct VirtT16Args {
     float* agg_v;
     float* trans_v;
     float* vsum;
+    int g_smem;     // the launch reserved V16_GROUPS * C * 68 floats behind V16_SMEM_BYTES for the G rows of the current graph
 };
 
+#ifndef V16_HN_TMA
+#define V16_HN_TMA 0            // 1: the tile's Hn block arrives by one TMA bulk copy a tile ahead; 0: LDG behind an L1 prefetch.
+#endif                          // r02: under ncu (caches flushed) the LDG form shows ~700 cycles of exposed latency per 16-column
+                                // chunk and the TMA form halves it, but in the bench (Hn just written by the node kernel, L2-warm)
+                                // the TMA form is 2 % SLOWER (1.627 vs 1.594 ms) -> default 0
+#ifndef V16_G_SMEM
+#define V16_G_SMEM 1            // 1: the G rows of the group's current graph (C x 64 floats) are cached in shared memory
+#endif
 constexpr int V16_THREADS = 512, V16_GROUPS = 4, V16_GROUP = 128;
 constexpr int V16_ROW = 68;
 constexpr int V16_MAXC = DISTEGNN_MAX_CHANNELS;
@@ -50,6 +61,7 @@ constexpr int V16_SMEM_BYTES = 6 * V16_W * 2                           // W2v, W
                                + V16_GROUPS * TILE_M * 4 * 4           // ΔX per row
                                + V16_GROUPS * 2 * TILE_M * 4           // φ_xv, φ_X per row
                                + V16_GROUPS * TILE_M * 4               // graph id per local node
+                               // + (launch time, if it fits) V16_GROUPS * C * V16_ROW * 4: G rows of the current graph
                                + 128;
 constexpr uint32_t V16_LBO = 1024;
 
@@ -75,7 +87,8 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     float* phi_all = dX_all + V16_GROUPS * TILE_M * 4;
     int* sgraph_all = reinterpret_cast<int*>(phi_all + V16_GROUPS * 2 * TILE_M);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sgraph_all + V16_GROUPS * TILE_M);
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + V16_GROUPS);
+    float* gs_all = reinterpret_cast<float*>(smem_raw + V16_SMEM_BYTES);      // present iff a.g_smem
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * V16_GROUPS);     // bars: [4] MMA done, [4] Hn block landed
 
     const int tid = threadIdx.x;
     const int grp = tid >> 7, t = tid & 127, wq = (tid >> 5) & 3;
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     }
     for (int i = tid; i < V16_GROUPS * (V16_MAXC * H + 4 * V16_MAXC); i += V16_THREADS) accH_all[i] = 0.f;
     if (tid == 0) {
-        for (int i = 0; i < V16_GROUPS; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 2 * V16_GROUPS; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -123,7 +136,11 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     float* dXs = dX_all + grp * TILE_M * 4;
     float* phis = phi_all + grp * 2 * TILE_M;
     int* sgraph = sgraph_all + grp * TILE_M;
+    float* gs = gs_all + grp * a.C * V16_ROW;          // [C][68]: pitch 68 keeps the channel rows of a node on distinct banks
+    const bool g_smem = V16_G_SMEM && a.g_smem;
     uint64_t* mbar = bars + grp;
+    uint64_t* hbar = bars + V16_GROUPS + grp;
+    uint32_t hph = 0;
     const uint32_t bar_id = 1 + grp;
     uint32_t mph = 0;
     int cur_graph = -1;
@@ -163,15 +180,29 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     };
 
     const int64_t num_tiles = (a.N + TN - 1) / TN;
-    for (int64_t tile = (int64_t)blockIdx.x * V16_GROUPS + grp; tile < num_tiles; tile += (int64_t)gridDim.x * V16_GROUPS) {
+    const int64_t tstride = (int64_t)gridDim.x * V16_GROUPS;
+    // Hn rows n0 .. n0+nvalid-1 of tile `tl` (contiguous, 256 B each) -> the start of the group's mv tile (thread 0 of the group)
+    auto fetch_hn = [&](int64_t tl) {
+        if (tl < num_tiles) {
+            const int64_t m0 = tl * TN;
+            const uint32_t bytes = (uint32_t)min((int64_t)TN, a.N - m0) * (H * 4);
+            mbar_expect_tx(hbar, bytes);
+            bulk_g2s(tile_s, a.Hn + (size_t)m0 * H, bytes, hbar);
+        }
+    };
+#if V16_HN_TMA
+    if (t == 0) fetch_hn((int64_t)blockIdx.x * V16_GROUPS + grp);
+#endif
+    for (int64_t tile = (int64_t)blockIdx.x * V16_GROUPS + grp; tile < num_tiles; tile += tstride) {
         const int64_t n0 = tile * TN;
         const int nvalid = (int)min((int64_t)TN, a.N - n0);
         const int rows = nvalid * C;
-        {   // pull the next tile's inputs (a contiguous block of Hn rows, x4, graph ids) into L1 while this one computes:
-            // stage 1 otherwise spends more than half of its time waiting for exactly these loads
-            const int64_t nn0 = (tile + (int64_t)gridDim.x * V16_GROUPS) * TN;
+        {   // pull the next tile's small inputs (x4, graph ids) into L1 while this one computes
+            const int64_t nn0 = (tile + tstride) * TN;
             const int nnv = (int)min((int64_t)TN, a.N - nn0);
+#if !V16_HN_TMA
             for (int i = t; i < 2 * nnv; i += V16_GROUP) prefetch_l1(a.Hn + (size_t)nn0 * H + 32 * i);
+#endif
             if (nnv > 0) {
                 if (t < (nnv * 16 + 127) / 128) prefetch_l1(a.x4 + (size_t)nn0 * 4 + 32 * t);
                 if (t == 127) prefetch_l1(a.batch + nn0);
@@ -185,6 +216,11 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         if (single && g_first != cur_graph) {
             flush(cur_graph);
             cur_graph = g_first;
+            if (g_smem)
+                for (int i = t; i < C * (H / 4); i += V16_GROUP) {       // G[g_first] -> shared (rare: once per graph and group)
+                    const int c = i / (H / 4), q = i - c * (H / 4);
+                    *reinterpret_cast<float4*>(gs + c * V16_ROW + 4 * q) = ldg4(a.G + ((size_t)g_first * C + c) * H + 4 * q);
+                }
             named_bar(bar_id, V16_GROUP);
         }
 
@@ -202,16 +238,32 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
             vr = sqrtf(dx * dx + dy * dy + dz * dz);
             *reinterpret_cast<float4*>(dXs + 4 * t) = make_float4(dx, dy, dz, 0.f);
         }
+#if V16_HN_TMA
+        mbar_wait(hbar, hph);                          // this tile's Hn block (requested during the previous tile)
+        hph ^= 1;
+        __syncwarp();
+        const float* hrow = tile_s + nl * H;
+        auto ld_h = [](const float* p) { return *reinterpret_cast<const ulonglong2*>(p); };
+#else
         const float* hrow = a.Hn + node * H;
+        auto ld_h = [](const float* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); };
+#endif
+#if V16_G_SMEM
+        // rows of the cached graph read shared memory, the others (tiles that straddle graphs) global memory: generic loads
+        const float* grow = (g_smem && g == cur_graph) ? (const float*)(gs + ch * V16_ROW) : a.G + ((size_t)g * C + ch) * H;
+        auto ld_g = [](const float* p) { return *reinterpret_cast<const ulonglong2*>(p); };
+#else
         const float* grow = a.G + ((size_t)g * C + ch) * H;
+        auto ld_g = [](const float* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); };
+#endif
         const f32x2 vr2 = bc2(vr);
         const float inv1 = tc16::encode_row2(
             [&](int c, f32x2 (&v)[8], bool, auto safe, float& qmax) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int cc = 16 * c + 4 * j4;
-                    const ulonglong2 hh = __ldg(reinterpret_cast<const ulonglong2*>(hrow + cc));
-                    const ulonglong2 gg = __ldg(reinterpret_cast<const ulonglong2*>(grow + cc));
+                    const ulonglong2 hh = ld_h(hrow + cc);
+                    const ulonglong2 gg = ld_g(grow + cc);
                     const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(w1rs + cc);
                     f32x2 p0 = fma2(vr2, wr.x, add2(hh.x, gg.x)), p1 = fma2(vr2, wr.y, add2(hh.y, gg.y));
                     silu4p<decltype(safe)::value>(p0, p1, qmax);
@@ -337,8 +389,14 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         };
         phis[t] = head(bxvs, w3xvs);
         fence_before_sync();
-        named_bar(bar_id, V16_GROUP);                  // D fully read (A still holds mv)
+#if V16_HN_TMA
+        fence_proxy_async_smem();                      // the pools' reads of the mv tile, ordered before the async refill below
+#endif
+        named_bar(bar_id, V16_GROUP);                  // D fully read (A still holds mv); nobody reads the mv tile any more
         issue(dWxhi, dWxlo);
+#if V16_HN_TMA
+        if (t == 0) fetch_hn(tile + tstride);
+#endif
         // trans_v[node] = mean_c(−ΔX_c·φ_xv,c) while MMA 3 runs
         for (int i = t; i < nvalid * 3; i += V16_GROUP) {
             const int n = i / 3, d = i - 3 * n;
@@ -399,12 +457,16 @@ extern "C" int distegnn_virtual_layer_fwd(int64_t n_nodes, int n_graphs, int A, 
     a.bx = layer_params + L.off[DISTEGNN_P_V_BX];
     a.w3x = layer_params + L.off[DISTEGNN_P_V_W3X];
     a.agg_v = agg_v; a.trans_v = trans_v; a.vsum = vsum;
-    ensure_dynamic_smem((const void*)virtual_layer_t16_kernel, (int)V16_SMEM_BYTES);
+    // the G cache is taken when it fits next to the fixed layout (C <= 8 at the current sizes)
+    const int g_bytes = V16_GROUPS * C * V16_ROW * 4;
+    a.g_smem = (V16_G_SMEM && V16_SMEM_BYTES + g_bytes <= 232448 - 1024) ? 1 : 0;
+    const int smem_bytes = V16_SMEM_BYTES + (a.g_smem ? g_bytes : 0);
+    ensure_dynamic_smem((const void*)virtual_layer_t16_kernel, (int)V16_SMEM_BYTES + V16_GROUPS * 8 * V16_ROW * 4);
     const int TN = TILE_M / C;
     const int64_t tiles = (n_nodes + TN - 1) / TN;
     int64_t grid = (tiles + V16_GROUPS - 1) / V16_GROUPS;
     if (grid > sm_count()) grid = sm_count();
-    virtual_layer_t16_kernel<<<(unsigned)grid, V16_THREADS, V16_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    virtual_layer_t16_kernel<<<(unsigned)grid, V16_THREADS, smem_bytes, (cudaStream_t)stream>>>(a);
     DEGNN_CHECK_LAUNCH();
     return DISTEGNN_OK;
 }

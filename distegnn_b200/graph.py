@@ -21,7 +21,7 @@ _MAX_TABLE = 1 << 27       # entries of the dense cell table (graphs x cells)
 
 def radius_graph(pos: Tensor, r: float, batch: Optional[Tensor] = None, loop: bool = False,
                  max_num_neighbors: Optional[int] = None, edge_attr_nf: int = 2) -> Tuple[Tensor, Tensor]:
-    """All ordered pairs (i, j), i != j unless `loop`, of the same graph with ‖pos_i − pos_j‖ <= r.
+    """All ordered pairs (i, j), i != j unless `loop`, of the same graph with ‖pos_i − pos_j‖ < r (strict, as torch_cluster).
 
     Returns (edge_index [2,E] int64 with edge_index[0] = i ascending, edge_attr [E, edge_attr_nf] fp32 = the edge length
     in every column — what distribute_graphs.py:44 builds).  `max_num_neighbors` is accepted for signature compatibility;

@@ -213,7 +213,7 @@ DISTEGNN_API int distegnn_virtual_layer_bwd(int64_t n_nodes, int n_graphs, int A
  * radius, ix = (int)((x - origin_x) * (1/cell)) clamped to the grid) and passes `order` (node ids in key order) and the
  * dense table cell_start[n_graphs*ncell + 1] (first position of every key).  origin_host[3] / dims_host[3] are HOST
  * arrays.  Two phases because the edge count is only known after the first:
- *   distegnn_radius_count -> deg[i] = number of j (same graph, j != i unless loop) with |x_i - x_j| <= radius
+ *   distegnn_radius_count -> deg[i] = number of j (same graph, j != i unless loop) with |x_i - x_j| < radius
  *   caller: rowptr = exclusive prefix sum of deg (int64 [N+1]), allocates E = rowptr[N] entries
  *   distegnn_radius_fill  -> row[e] = i, col[e] = j for e in [rowptr[i], rowptr[i+1]), dist[e] = |x_i - x_j| (dist may be
  *                            NULL): edges grouped by destination row, rows ascending. */
