@@ -78,6 +78,12 @@ struct EdgeCsArgs {
 #ifndef CS_S1_UNROLL
 #define CS_S1_UNROLL 2          // chunks (of 8 columns) of stage 1 unrolled together (P / Q loads of both in flight)
 #endif
+#ifndef CS_SEGSUM_FAST
+#define CS_SEGSUM_FAST 1        // 1: warps whose 16 edges all share one destination row take a test-free summation path
+#endif
+#ifndef CS_DEFER_AGGX
+#define CS_DEFER_AGGX 0         // 1: the shuffle reduction + RED.ADD of Δx·φ of tile i runs in the MMA-1 window of tile i+1
+#endif
 #ifndef CS_X_STAGED
 #define CS_X_STAGED 1           // 1: the next tile's coordinates x[row], x[col] are gathered by cp.async into shared memory (one
 #endif                          // copy per edge, issued after the stage-1 barrier, visible to both column halves after the
@@ -289,6 +295,24 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         }
     };
 
+    // Δx·φ_half summed over runs of equal destination row inside the warp (rows are sorted), one RED.ADD triple per run
+    auto reduce_aggx = [&](float sx, float sy, float sz, int rw) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int rk = __shfl_up_sync(FULL, rw, o);
+            const float ox = __shfl_up_sync(FULL, sx, o), oy = __shfl_up_sync(FULL, sy, o), oz = __shfl_up_sync(FULL, sz, o);
+            if (lane >= o && rk == rw) { sx += ox; sy += oy; sz += oz; }
+        }
+        const int rnext = __shfl_down_sync(FULL, rw, 1);
+        if (rw >= 0 && (lane == 31 || rnext != rw)) {
+            float* dst = a.agg_x + (size_t)rw * 4;
+            atomicAdd(dst + 0, sx);
+            atomicAdd(dst + 1, sy);
+            atomicAdd(dst + 2, sz);
+        }
+    };
+    float dfx = 0.f, dfy = 0.f, dfz = 0.f;      // CS_DEFER_AGGX: the previous tile's Δx·φ_half of this thread's edge
+
     // ---- prologue: first tile read directly, its Q rows fetched, the second tile's indices staged ---------------
     if (tile < num_tiles) {
         const int64_t e = tile * TILE_M + r;
@@ -443,6 +467,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
 #endif
         }
         if (nvalid_r) prefetch_l1(a.P + (size_t)nrow_s[r] * H + cb);      // one 128-byte line per thread
+#if CS_DEFER_AGGX
+        // the previous tile's coordinate aggregation, here because the group would otherwise idle until MMA 1 completes
+        // (its destination rows are still in the other parity slot of srow)
+        if (it > 0) reduce_aggx(dfx, dfy, dfz, srow2[((it - 1) & 1) * TILE_M + r]);
+#endif
 
         mbar_wait(mbar, 0);
         __syncwarp();
@@ -558,17 +587,30 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
                 }
             };
             f32x2 s0 = *reinterpret_cast<const f32x2*>(colp);
+#if CS_SEGSUM_FAST
+            if ((M >> 1) == 0u) {       // no run starts inside the warp's 16 edges (about half of the warps at degree 20):
+                f32x2 s1 = *reinterpret_cast<const f32x2*>(colp + cs_qoff(1));     // two plain chains, no per-edge test
 #pragma unroll
-            for (int e = 1; e < 16; ++e) {
-                const f32x2 v = *reinterpret_cast<const f32x2*>(colp + cs_qoff(e));
-                if ((M >> e) & 1u) {
-                    flush(s0, e - 1);
-                    s0 = v;
-                } else {
-                    s0 = add2(s0, v);
+                for (int e = 2; e < 16; e += 2) {
+                    s0 = add2(s0, *reinterpret_cast<const f32x2*>(colp + cs_qoff(e)));
+                    s1 = add2(s1, *reinterpret_cast<const f32x2*>(colp + cs_qoff(e + 1)));
                 }
+                flush(add2(s0, s1), 15);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int e = 1; e < 16; ++e) {
+                    const f32x2 v = *reinterpret_cast<const f32x2*>(colp + cs_qoff(e));
+                    if ((M >> e) & 1u) {
+                        flush(s0, e - 1);
+                        s0 = v;
+                    } else {
+                        s0 = add2(s0, v);
+                    }
+                }
+                flush(s0, 15);
             }
-            flush(s0, 15);
 #else
             uint32_t M = ((rmask[wk >> 1] >> (16 * (wk & 1))) & 0xffffu) | 1u;
             while (M) {
@@ -702,23 +744,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             p_first[1] = __ldg(reinterpret_cast<const ulonglong2*>(pn + 4));
         }
 #endif
-        {
-            float sx = dx * phi, sy = dy * phi, sz = dz * phi;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int rk = __shfl_up_sync(FULL, row_c, o);
-                const float ox = __shfl_up_sync(FULL, sx, o), oy = __shfl_up_sync(FULL, sy, o),
-                            oz = __shfl_up_sync(FULL, sz, o);
-                if (lane >= o && rk == row_c) { sx += ox; sy += oy; sz += oz; }
-            }
-            const int rnext = __shfl_down_sync(FULL, row_c, 1);
-            if (row_c >= 0 && (lane == 31 || rnext != row_c)) {
-                float* dst = a.agg_x + (size_t)row_c * 4;
-                atomicAdd(dst + 0, sx);
-                atomicAdd(dst + 1, sy);
-                atomicAdd(dst + 2, sz);
-            }
-        }
+#if CS_DEFER_AGGX
+        dfx = dx * phi; dfy = dy * phi; dfz = dz * phi;      // reduced and added to agg_x in the next MMA-1 window (or the epilogue)
+#else
+        reduce_aggx(dx * phi, dy * phi, dz * phi, row_c);
+#endif
 
         // ---- roll the next tile's edge into place -------------------------------------------------------------
         row_c = row_n;
@@ -747,6 +777,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
         set_geometry(xi_n, xj_n);
     }
 
+#if CS_DEFER_AGGX
+    {   // the last tile's deferred aggregation (it_done tiles were processed by this group)
+        const int64_t first = (int64_t)blockIdx.x * CS_GROUPS + grp;
+        const int64_t it_done = first < num_tiles ? (num_tiles - first + stride - 1) / stride : 0;
+        if (it_done > 0) reduce_aggx(dfx, dfy, dfz, srow2[((it_done - 1) & 1) * TILE_M + r]);
+    }
+#endif
     fence_before_sync();
     __syncthreads();
     if ((tid >> 5) == 0) tmem_dealloc(tbase, 512);

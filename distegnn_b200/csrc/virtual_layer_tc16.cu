@@ -46,6 +46,9 @@ struct VirtT16Args {
 #endif                          // r02: under ncu (caches flushed) the LDG form shows ~700 cycles of exposed latency per 16-column
                                 // chunk and the TMA form halves it, but in the bench (Hn just written by the node kernel, L2-warm)
                                 // the TMA form is 2 % SLOWER (1.627 vs 1.594 ms) -> default 0
+#ifndef V16_TDOMAIN
+#define V16_TDOMAIN 1           // 1: stages 2, 3a, 3b run in the "t domain" (common.cuh silu4t): W2v and the biases carry −log2(e),
+#endif                          // the head weights and every consumer of mv (means, per-graph sums) carry −ln 2
 #ifndef V16_G_SMEM
 #define V16_G_SMEM 1            // 1: the G rows of the group's current graph (C x 64 floats) are cached in shared memory
 #endif
@@ -64,6 +67,7 @@ constexpr int V16_SMEM_BYTES = 6 * V16_W * 2                           // W2v, W
                                // + (launch time, if it fits) V16_GROUPS * C * V16_ROW * 4: G rows of the current graph
                                + 128;
 constexpr uint32_t V16_LBO = 1024;
+constexpr float kVIn = V16_TDOMAIN ? SILU_T_IN : 1.0f, kVOut = V16_TDOMAIN ? SILU_T_OUT : 1.0f;
 
 __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const VirtT16Args a) {
     using namespace umma;
@@ -98,16 +102,16 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     const int TN = TILE_M / C;
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, V16_THREADS);
+    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, V16_THREADS, kVIn);     // t2 = kVIn·(a1·W2vᵀ + b2v); mv' = kVIn·mv
     tc16::stage_weight(Wxvhi, Wxvlo, a.wxv, 0, 64, tid, V16_THREADS);
     tc16::stage_weight(Wxhi, Wxlo, a.wx, 0, 64, tid, V16_THREADS);
     if (tid < H) {
         w1rs[tid] = a.w1r[tid];
-        b2s[tid] = a.b2[tid];
-        bxvs[tid] = a.bxv[tid];
-        w3xvs[tid] = a.w3xv[tid];
-        bxs[tid] = a.bx[tid];
-        w3xs[tid] = a.w3x[tid];
+        b2s[tid] = a.b2[tid] * kVIn;
+        bxvs[tid] = a.bxv[tid] * kVIn;              // t3 = mv'·Wᵀ + kVIn·b  (kVIn·kVOut = 1: the 64x64 head weights stay as they are)
+        w3xvs[tid] = a.w3xv[tid] * kVOut;
+        bxs[tid] = a.bx[tid] * kVIn;
+        w3xs[tid] = a.w3x[tid] * kVOut;
     }
     for (int i = tid; i < V16_GROUPS * (V16_MAXC * H + 4 * V16_MAXC); i += V16_THREADS) accH_all[i] = 0.f;
     if (tid == 0) {
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
             float* dst = a.vsum + (size_t)g * K;
             if (need_feat)
                 for (int i = t; i < C * H; i += V16_GROUP) {
-                    atomicAdd(dst + 4 + 3 * C + i, accH[i]);
+                    atomicAdd(dst + 4 + 3 * C + i, accH[i] * kVOut);
                     accH[i] = 0.f;
                 }
             if (t < 3 * C) {
@@ -287,7 +291,11 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(b2s + cc);
                     f32x2 m0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
                     f32x2 m1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+#if V16_TDOMAIN
+                    silu4t<decltype(safe)::value>(m0, m1, qmax);
+#else
                     silu4p<decltype(safe)::value>(m0, m1, qmax);
+#endif
                     if (first && need_feat) *reinterpret_cast<ulonglong2*>(myrow + cc) = make_ulonglong2(m0, m1);
                     v[2 * j4] = m0;
                     v[2 * j4 + 1] = m1;
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
             // thread <-> (column pair, quarter): one LDS.64 + one FADD2 per two elements, two chains per sum
             const int c2 = 2 * (t & 31), q4 = t >> 5;
             auto ld2 = [](const float* p) { return *reinterpret_cast<const f32x2*>(p); };
-            const f32x2 invC2 = bc2(1.0f / (float)C);
+            const f32x2 invC2 = bc2(kVOut / (float)C);          // the tile holds mv' = kVIn·mv
             for (int n = q4; n < nvalid; n += 4) {          // mean over channels per node
                 const float* base = tile_s + (n * C) * V16_ROW + c2;
                 f32x2 s0 = 0ull, s1 = 0ull;
@@ -333,8 +341,8 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     for (int c = 0; c < C; ++c) {
                         float v0, v1;
                         upk2(ld2(tile_s + (n * C + c) * V16_ROW + c2), v0, v1);
-                        atomicAdd(dst + c * H, v0);
-                        atomicAdd(dst + c * H + 1, v1);
+                        atomicAdd(dst + c * H, v0 * kVOut);
+                        atomicAdd(dst + c * H + 1, v1 * kVOut);
                     }
                 }
             }
@@ -353,7 +361,11 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     const ulonglong2 ww = *reinterpret_cast<const ulonglong2*>(ws + cc);
                     f32x2 s0 = fma2(pk2u(d[4 * j4 + 0], d[4 * j4 + 1]), is2, bb.x);
                     f32x2 s1 = fma2(pk2u(d[4 * j4 + 2], d[4 * j4 + 3]), is2, bb.y);
+#if V16_TDOMAIN
+                    silu4t<decltype(safe)::value>(s0, s1, qmax);
+#else
                     silu4p<decltype(safe)::value>(s0, s1, qmax);
+#endif
                     ph01 = fma2(s0, ww.x, ph01);
                     ph23 = fma2(s1, ww.y, ph23);
                 }
