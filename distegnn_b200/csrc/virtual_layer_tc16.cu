@@ -46,6 +46,9 @@ struct VirtT16Args {
 #endif                          // r02: under ncu (caches flushed) the LDG form shows ~700 cycles of exposed latency per 16-column
                                 // chunk and the TMA form halves it, but in the bench (Hn just written by the node kernel, L2-warm)
                                 // the TMA form is 2 % SLOWER (1.627 vs 1.594 ms) -> default 0
+#ifndef V16_END_BARRIER
+#define V16_END_BARRIER 0       // 1: group barrier at the end of every tile (r01); 0: only for tiles that straddle two graphs
+#endif
 #ifndef V16_TDOMAIN
 #define V16_TDOMAIN 1           // 1: stages 2, 3a, 3b run in the "t domain" (common.cuh silu4t): W2v and the biases carry −log2(e),
 #endif                          // the head weights and every consumer of mv (means, per-graph sums) carry −ln 2
@@ -185,17 +188,19 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
 
     const int64_t num_tiles = (a.N + TN - 1) / TN;
     const int64_t tstride = (int64_t)gridDim.x * V16_GROUPS;
-    // Hn rows n0 .. n0+nvalid-1 of tile `tl` (contiguous, 256 B each) -> the start of the group's mv tile (thread 0 of the group)
+    // Hn rows n0 .. n0+nvalid-1 of tile `tl` -> the start of the group's mv tile at the padded pitch V16_ROW (the channel rows
+    // of 4 different nodes that a warp reads together then sit on different banks): one 256-byte bulk copy per node, issued by
+    // the first `nvalid` threads of the group; thread 0 posts the byte count
     auto fetch_hn = [&](int64_t tl) {
         if (tl < num_tiles) {
             const int64_t m0 = tl * TN;
-            const uint32_t bytes = (uint32_t)min((int64_t)TN, a.N - m0) * (H * 4);
-            mbar_expect_tx(hbar, bytes);
-            bulk_g2s(tile_s, a.Hn + (size_t)m0 * H, bytes, hbar);
+            const int nv = (int)min((int64_t)TN, a.N - m0);
+            if (t == 0) mbar_expect_tx(hbar, (uint32_t)nv * (H * 4));     // may land after the first bytes: the count just dips below 0
+            if (t < nv) bulk_g2s(tile_s + t * V16_ROW, a.Hn + (size_t)(m0 + t) * H, H * 4, hbar);
         }
     };
 #if V16_HN_TMA
-    if (t == 0) fetch_hn((int64_t)blockIdx.x * V16_GROUPS + grp);
+    fetch_hn((int64_t)blockIdx.x * V16_GROUPS + grp);
 #endif
     for (int64_t tile = (int64_t)blockIdx.x * V16_GROUPS + grp; tile < num_tiles; tile += tstride) {
         const int64_t n0 = tile * TN;
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         mbar_wait(hbar, hph);                          // this tile's Hn block (requested during the previous tile)
         hph ^= 1;
         __syncwarp();
-        const float* hrow = tile_s + nl * H;
+        const float* hrow = tile_s + nl * V16_ROW;
         auto ld_h = [](const float* p) { return *reinterpret_cast<const ulonglong2*>(p); };
 #else
         const float* hrow = a.Hn + node * H;
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         named_bar(bar_id, V16_GROUP);                  // D fully read (A still holds mv); nobody reads the mv tile any more
         issue(dWxhi, dWxlo);
 #if V16_HN_TMA
-        if (t == 0) fetch_hn(tile + tstride);
+        fetch_hn(tile + tstride);
 #endif
         // trans_v[node] = mean_c(−ΔX_c·φ_xv,c) while MMA 3 runs
         for (int i = t; i < nvalid * 3; i += V16_GROUP) {
@@ -434,7 +439,9 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
                     atomicAdd(a.vsum + (size_t)sgraph[n] * K + 4 + t, dXs[4 * (n * C + c) + d] * phx[n * C + c]);
             }
         }
-        named_bar(bar_id, V16_GROUP);                  // sgraph/dXs/phis/tile_s are rewritten by the next tile
+        // dXs / phis / the mv tile are rewritten by the next tile only after ITS first group barrier, which the threads of the
+        // loop above reach after their reads; sgraph is rewritten before that barrier, and read above only on the straddling path
+        if (V16_END_BARRIER || !single) named_bar(bar_id, V16_GROUP);
     }
     flush(cur_graph);
 
