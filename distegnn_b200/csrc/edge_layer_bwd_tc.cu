@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) edge_layer_bwd_tc_kernel(const 
     const bool need_m = !(a.flags & DISTEGNN_FLAG_LAST) && a.g_aggm != nullptr;
 
     // ---- one-time setup -------------------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, BT_THREADS);
-    tc16::stage_weight(Wchi, Wclo, a.wc, 0, 64, tid, BT_THREADS);
+    tc16::stage_weight<BT_THREADS>(W2hi, W2lo, a.w2, 0, 64, tid);
+    tc16::stage_weight<BT_THREADS>(Wchi, Wclo, a.wc, 0, 64, tid);
     stage_weight_t(W2Thi, W2Tlo, a.w2, tid, BT_THREADS);
     stage_weight_t(WcThi, WcTlo, a.wc, tid, BT_THREADS);
     if (tid < H) {

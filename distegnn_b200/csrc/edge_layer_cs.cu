@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
     constexpr bool need_m = !LASTL;        // the last layer only moves coordinates (DISTEGNN_FLAG_LAST): no segment sum of m
 
     // ---- one-time setup -------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, CS_THREADS, kTIn);     // t2 = kTIn·(a1·W2ᵀ + b2)
-    tc16::stage_weight(Wchi, Wclo, a.wc, 0, 64, tid, CS_THREADS);           // t3 = s2·Wcᵀ + kTIn·bc  (kTIn·kTOut = 1)
+    tc16::stage_weight<CS_THREADS>(W2hi, W2lo, a.w2, 0, 64, tid, kTIn);     // t2 = kTIn·(a1·W2ᵀ + b2)
+    tc16::stage_weight<CS_THREADS>(Wchi, Wclo, a.wc, 0, 64, tid);           // t3 = s2·Wcᵀ + kTIn·bc  (kTIn·kTOut = 1)
     if (tid < H) {
         b2s[tid] = a.b2[tid] * kTIn;
         bcs[tid] = a.bc[tid] * kTIn;

@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(NT_THREADS, 1) node_layer_tc_kernel(const Node
     const int Na = a.Na;
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    tc16::stage_weight(Lhi, Llo, a.lw, 0, 64, tid, NT_THREADS);
+    tc16::stage_weight<NT_THREADS>(Lhi, Llo, a.lw, 0, 64, tid);
     if (!last) {
-        for (int c = 0; c < 3; ++c) tc16::stage_weight(N1hi + c * NT_W, N1lo + c * NT_W, a.n1 + c * H * H, 0, 64, tid, NT_THREADS);
-        tc16::stage_weight(N2hi, N2lo, a.n2, 0, 64, tid, NT_THREADS);
-        tc16::stage_weight(NXhi, NXlo, a.nw1a, 0, 192, tid, NT_THREADS);
-        tc16::stage_weight(NXhi, NXlo, a.nw1b, 64, 192, tid, NT_THREADS);
-        tc16::stage_weight(NXhi, NXlo, a.nw1h, 128, 192, tid, NT_THREADS);
+        for (int c = 0; c < 3; ++c) tc16::stage_weight<NT_THREADS>(N1hi + c * NT_W, N1lo + c * NT_W, a.n1 + c * H * H, 0, 64, tid);
+        tc16::stage_weight<NT_THREADS>(N2hi, N2lo, a.n2, 0, 64, tid);
+        tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1a, 0, 192, tid);
+        tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1b, 64, 192, tid);
+        tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1h, 128, 192, tid);
     }
     if (tid < H) {
         lbs[tid] = a.lb[tid];
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) embed_tc_kernel(const EmbedTcAr
     const int grp = tid >> 7, t = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
     const int F = a.F;
 
-    tc16::stage_weight(NXhi, NXlo, a.nw1a, 0, 192, tid, NT_THREADS);
-    tc16::stage_weight(NXhi, NXlo, a.nw1b, 64, 192, tid, NT_THREADS);
-    tc16::stage_weight(NXhi, NXlo, a.nw1h, 128, 192, tid, NT_THREADS);
+    tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1a, 0, 192, tid);
+    tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1b, 64, 192, tid);
+    tc16::stage_weight<NT_THREADS>(NXhi, NXlo, a.nw1h, 128, 192, tid);
     for (int i = tid; i < F * H; i += NT_THREADS) wts[i] = a.wt[i];
     if (tid < H) {
         bs[tid] = a.bias[tid];

@@ -47,16 +47,37 @@ __device__ __forceinline__ void split_pair(f32x2 x, uint32_t& hi, uint32_t& lo) 
 }
 
 // stage W[n][k] (given k-major: wt[k*64+n]) as rows n_off..n_off+63 of an N_total-row B operand, fp16 hi/lo
+// NTHREADS is a template parameter so that the H·H / NTHREADS loads of a thread are all issued before the first conversion
+// (a rolled load -> convert -> store loop pays one global round trip per element: r02 ncu showed the node kernel spending
+// 5 % of its time — 33 µs — in this prologue, 8 matrices x 16 dependent trips per thread).
+#ifndef TC16_STAGE_BATCH
+#define TC16_STAGE_BATCH 1
+#endif
+template <int NTHREADS>
 __device__ __forceinline__ void stage_weight(__half* hi, __half* lo, const float* __restrict__ wt_kmajor, int n_off,
-                                             int n_total, int tid, int nthreads, float scale = 1.0f) {
+                                             int n_total, int tid, float scale = 1.0f) {
+    static_assert((H * H) % NTHREADS == 0, "thread count must divide the matrix");
+    constexpr int R = H * H / NTHREADS;
     const uint32_t lbo_h = (uint32_t)(n_total / 8) * 64u;     // halfs per K chunk of 8
-    for (int i = tid; i < H * H; i += nthreads) {
+#if TC16_STAGE_BATCH
+    float w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) w[r] = __ldg(wt_kmajor + tid + r * NTHREADS);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#else
+    float w[1];
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+        w[0] = __ldg(wt_kmajor + tid + r * NTHREADS);
+#endif
+        const int i = tid + r * NTHREADS;
         const int k = i >> 6, n = (i & 63) + n_off;
-        const float w = __ldg(wt_kmajor + i) * scale;
-        const __half h = __float2half_rn(w);
+        const float ws = w[TC16_STAGE_BATCH ? r : 0] * scale;
+        const __half h = __float2half_rn(ws);
         const uint32_t o = (uint32_t)(k >> 3) * lbo_h + (uint32_t)(n >> 3) * 64u + (uint32_t)(n & 7) * 8u + (k & 7);
         hi[o] = h;
-        lo[o] = __float2half_rn(w - __half2float(h));
+        lo[o] = __float2half_rn(ws - __half2float(h));
     }
 }
 __host__ __device__ constexpr uint32_t lbo_bytes(int n_total) { return (uint32_t)(n_total / 8) * 128u; }

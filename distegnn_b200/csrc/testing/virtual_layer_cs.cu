@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(VC_THREADS, 1) virtual_layer_cs_kernel(const V
     const int TN = TILE_M / C;
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, VC_THREADS);
-    tc16::stage_weight(Wxvhi, Wxvlo, a.wxv, 0, 64, tid, VC_THREADS);
-    tc16::stage_weight(Wxhi, Wxlo, a.wx, 0, 64, tid, VC_THREADS);
+    tc16::stage_weight<VC_THREADS>(W2hi, W2lo, a.w2, 0, 64, tid);
+    tc16::stage_weight<VC_THREADS>(Wxvhi, Wxvlo, a.wxv, 0, 64, tid);
+    tc16::stage_weight<VC_THREADS>(Wxhi, Wxlo, a.wx, 0, 64, tid);
     if (tid < H) {
         w1rs[tid] = a.w1r[tid];
         b2s[tid] = a.b2[tid];

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     const int TN = TILE_M / C;
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    tc16::stage_weight(W2hi, W2lo, a.w2, 0, 64, tid, V16_THREADS, kVIn);     // t2 = kVIn·(a1·W2vᵀ + b2v); mv' = kVIn·mv
-    tc16::stage_weight(Wxvhi, Wxvlo, a.wxv, 0, 64, tid, V16_THREADS);
-    tc16::stage_weight(Wxhi, Wxlo, a.wx, 0, 64, tid, V16_THREADS);
+    tc16::stage_weight<V16_THREADS>(W2hi, W2lo, a.w2, 0, 64, tid, kVIn);     // t2 = kVIn·(a1·W2vᵀ + b2v); mv' = kVIn·mv
+    tc16::stage_weight<V16_THREADS>(Wxvhi, Wxvlo, a.wxv, 0, 64, tid);
+    tc16::stage_weight<V16_THREADS>(Wxhi, Wxlo, a.wx, 0, 64, tid);
     if (tid < H) {
         w1rs[tid] = a.w1r[tid];
         b2s[tid] = a.b2[tid] * kVIn;
