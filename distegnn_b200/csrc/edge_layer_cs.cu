@@ -21,8 +21,14 @@
 // The range rescue needs ONE scale per row, i.e. agreement between the two warps that share it: every warp posts
 // an "anything out of range" flag before the group barrier that precedes the MMA; if any flag is set the whole
 // group takes the cold path (row maxima exchanged through shared memory, two more barriers).
-// The next tile's (row, col, edge_attr) are staged into shared memory with LDGSTS one stage ahead (double
-// buffered), its Q rows by TMA bulk copies issued 16 per warp from those staged indices.
+// Everything a tile needs from memory is requested at least one stage ahead, so that no warp waits on a round trip (r02: the
+// three places where one did were 10 % of the kernel):
+//   (row, col, edge_attr) of tile i+1   LDGSTS at the start of stage 1 of tile i (double buffered)
+//   Q[col] rows of tile i+1             TMA tile::gather4, four rows per instruction, after the segment sum of tile i
+//   x[row], x[col] of tile i+1          one cp.async pair per edge after the stage-1 barrier, read by both halves at the tile end
+//   P[row] of tile i+1, chunk 0         LDG at the end of stage 3 of tile i; chunk j+1 before the math of chunk j
+// Stages 2 and 3 run in the "t domain" (common.cuh silu4t): −log2(e) is folded into W2 and the biases, −ln 2 into w3 and
+// the segment-sum flush, so the SiLU never forms its exponent argument explicitly.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <string.h>

@@ -10,8 +10,8 @@
 // All three 64x64 layers run as kind::f16 tile GEMMs with the fp16 2-term split (tc16.cuh); TMEM per group:
 // A_hi 32 + A_lo 32 + D 64 columns (the two coordinate heads reuse D one after the other).
 //   stage 1  a1 = SiLU(Hn[node] + G[graph,c] + w_r·‖ΔX‖)  -> A              MMA 1: D = a1·W2vᵀ
-//            (the tile's Hn rows — one contiguous block — arrive by ONE TMA bulk copy issued a tile ahead into the mv
-//             tile's shared memory, which is idle between the pools of mv and the next tile's stage 2: V16_HN_TMA)
+//            (the C x 64 G rows of the group's current graph are cached in shared memory: every (node, channel) row re-read
+//             its G row through an L1 that shared memory leaves ~20 KB of — r02: −15 % kernel time; V16_G_SMEM)
 //   stage 2  mv = SiLU(D + b2v) -> shared tile + A                            MMA 2: D = mv·Wxvᵀ
 //            (while it runs: agg_v[node] = mean_c mv, per-graph Σ_i mv accumulated in shared memory)
 //   stage 3a φ_xv = w3xv·SiLU(D + bxv)                                        MMA 3: D = mv·WXᵀ
