@@ -46,6 +46,9 @@ struct VirtT16Args {
 #endif                          // r02: under ncu (caches flushed) the LDG form shows ~700 cycles of exposed latency per 16-column
                                 // chunk and the TMA form halves it, but in the bench (Hn just written by the node kernel, L2-warm)
                                 // the TMA form is 2 % SLOWER (1.627 vs 1.594 ms) -> default 0
+#ifndef V16_SHFL_ACCX
+#define V16_SHFL_ACCX 1         // 1: per-graph Σ ΔX·φ_X by warp butterflies + shared atomics when C is a power of two (no barrier)
+#endif
 #ifndef V16_END_BARRIER
 #define V16_END_BARRIER 0       // 1: group barrier at the end of every tile (r01); 0: only for tiles that straddle two graphs
 #endif
@@ -103,6 +106,8 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
     const int K = 4 + 3 * C + H * C;
     const bool need_feat = !(a.flags & DISTEGNN_FLAG_LAST);
     const int TN = TILE_M / C;
+    const bool pow2C = (C & (C - 1)) == 0 && C <= 32;
+    const int lane = tid & 31;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     tc16::stage_weight<V16_THREADS>(W2hi, W2lo, a.w2, 0, 64, tid, kVIn);     // t2 = kVIn·(a1·W2vᵀ + b2v); mv' = kVIn·mv
@@ -424,25 +429,44 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         mma_done();
 
         // ---- stage 3b: φ_X = w3x·SiLU(D + bx); Σ_i ΔX_ic·φ_X,ic per graph [3][C] -----------------------------
-        phis[TILE_M + t] = head(bxs, w3xs);
+        const float phiX = head(bxs, w3xs);
         fence_before_sync();
-        named_bar(bar_id, V16_GROUP);
-        if (t < 3 * C) {
-            const int d = t / C, c = t - d * C;
-            const float* phx = phis + TILE_M;
-            if (single) {
-                float s = 0.f;
-                for (int n = 0; n < nvalid; ++n) s = fmaf(dXs[4 * (n * C + c) + d], phx[n * C + c], s);
-                accX[t] += s;
-            } else {
-                for (int n = 0; n < nvalid; ++n)
-                    atomicAdd(a.vsum + (size_t)sgraph[n] * K + 4 + t, dXs[4 * (n * C + c) + d] * phx[n * C + c]);
+        if (V16_SHFL_ACCX && single && pow2C) {
+            // rows of one channel sit C lanes apart: butterfly over the lane bits above log2(C), then one shared-memory atomic per
+            // (component, channel) and warp — no group barrier, no serial loop on the critical path of the tile
+            const float4 d4 = *reinterpret_cast<const float4*>(dXs + 4 * t);      // own ΔX, written by this thread in stage 1
+            float sx = rvalid ? d4.x * phiX : 0.f, sy = rvalid ? d4.y * phiX : 0.f, sz = rvalid ? d4.z * phiX : 0.f;
+            for (int o = C; o < 32; o <<= 1) {
+                sx += __shfl_xor_sync(FULL, sx, o);
+                sy += __shfl_xor_sync(FULL, sy, o);
+                sz += __shfl_xor_sync(FULL, sz, o);
+            }
+            if (lane < C) {
+                atomicAdd(accX + lane, sx);
+                atomicAdd(accX + C + lane, sy);
+                atomicAdd(accX + 2 * C + lane, sz);
+            }
+        } else {
+            phis[TILE_M + t] = phiX;
+            named_bar(bar_id, V16_GROUP);
+            if (t < 3 * C) {
+                const int d = t / C, c = t - d * C;
+                const float* phx = phis + TILE_M;
+                if (single) {
+                    float s = 0.f;
+                    for (int n = 0; n < nvalid; ++n) s = fmaf(dXs[4 * (n * C + c) + d], phx[n * C + c], s);
+                    accX[t] += s;
+                } else {
+                    for (int n = 0; n < nvalid; ++n)
+                        atomicAdd(a.vsum + (size_t)sgraph[n] * K + 4 + t, dXs[4 * (n * C + c) + d] * phx[n * C + c]);
+                }
             }
         }
         // dXs / phis / the mv tile are rewritten by the next tile only after ITS first group barrier, which the threads of the
         // loop above reach after their reads; sgraph is rewritten before that barrier, and read above only on the straddling path
         if (V16_END_BARRIER || !single) named_bar(bar_id, V16_GROUP);
     }
+    named_bar(bar_id, V16_GROUP);      // the last tile's shared-memory atomics into accX, before other threads flush them
     flush(cur_graph);
 
     fence_before_sync();
