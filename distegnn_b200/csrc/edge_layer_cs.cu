@@ -84,6 +84,9 @@ struct EdgeCsArgs {
 #ifndef CS_S1_UNROLL
 #define CS_S1_UNROLL 2          // chunks (of 8 columns) of stage 1 unrolled together (P / Q loads of both in flight)
 #endif
+#ifndef CS_P_PREFETCH
+#define CS_P_PREFETCH 1         // L1 prefetch of the next tile's P rows in the MMA-1 window (r01; kept next to CS_P_AHEAD)
+#endif
 #ifndef CS_SEGSUM_FAST
 #define CS_SEGSUM_FAST 1        // 1: warps whose 16 edges all share one destination row take a test-free summation path
 #endif
@@ -472,7 +475,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) edge_layer_cs_kernel(const Edge
             cp_async_commit();
 #endif
         }
+#if CS_P_PREFETCH
         if (nvalid_r) prefetch_l1(a.P + (size_t)nrow_s[r] * H + cb);      // one 128-byte line per thread
+#endif
 #if CS_DEFER_AGGX
         // the previous tile's coordinate aggregation, here because the group would otherwise idle until MMA 1 completes
         // (its destination rows are still in the other parity slot of srow)

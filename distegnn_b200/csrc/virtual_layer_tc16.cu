@@ -46,6 +46,9 @@ struct VirtT16Args {
 #endif                          // r02: under ncu (caches flushed) the LDG form shows ~700 cycles of exposed latency per 16-column
                                 // chunk and the TMA form halves it, but in the bench (Hn just written by the node kernel, L2-warm)
                                 // the TMA form is 2 % SLOWER (1.627 vs 1.594 ms) -> default 0
+#ifndef V16_HN_PREFETCH
+#define V16_HN_PREFETCH 1       // L1 prefetch of the next tile's Hn rows at the start of a tile
+#endif
 #ifndef V16_SHFL_ACCX
 #define V16_SHFL_ACCX 1         // 1: per-graph Σ ΔX·φ_X by warp butterflies + shared atomics when C is a power of two (no barrier)
 #endif
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(V16_THREADS, 1) virtual_layer_t16_kernel(const
         {   // pull the next tile's small inputs (x4, graph ids) into L1 while this one computes
             const int64_t nn0 = (tile + tstride) * TN;
             const int nnv = (int)min((int64_t)TN, a.N - nn0);
-#if !V16_HN_TMA
+#if !V16_HN_TMA && V16_HN_PREFETCH
             for (int i = t; i < 2 * nnv; i += V16_GROUP) prefetch_l1(a.Hn + (size_t)nn0 * H + 32 * i);
 #endif
             if (nnv > 0) {
